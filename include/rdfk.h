@@ -1,0 +1,128 @@
+/*
+ * rdfk.h -- C ABI of librdfk.so: the B200 (sm_100a) pair-distance histogram
+ * kernels behind pmda.rdf.InterRDF / InterRDF_s.
+ *
+ * The reference (MDAnalysis/pmda) is pure Python and has no FFI for this path;
+ * the boundary it crosses into native code is the pair of calls
+ *
+ *     pairs, dist = MDAnalysis.lib.distances.capped_distance(
+ *                       g1.positions, g2.positions, maxrange, box=u.dimensions)
+ *     count = np.histogram(dist, bins=nbins, range=range)[0]
+ *
+ * at pmda/rdf.py:123-134 (InterRDF._single_frame) and pmda/rdf.py:298-305
+ * (InterRDF_s._single_frame).  Each entry point below replaces that pair of
+ * calls for a whole *block of frames* (the unit pmda/parallel.py:429-439 loops
+ * over), so one call == one `_dask_helper` block body.  INTEGRATION.md shows
+ * the ctypes stub a pmda maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a CUDA *device* pointer unless the
+ *     name ends in `_host`.  `stream` is a cudaStream_t passed as void*.
+ *   - the caller owns every buffer, including the scratch `workspace`
+ *     (size from the matching *_workspace_bytes query, 256-byte aligned).
+ *   - launches are asynchronous on `stream`; nothing synchronises.
+ *   - every function returns 0 on success, a negative RDFK_E* code on error;
+ *     rdfk_last_error() returns a thread-local message.  Nothing throws,
+ *     nothing calls exit().
+ *   - re-entrant from several host threads on different streams/devices; the
+ *     library keeps no mutable global state besides per-device function
+ *     attributes and the thread-local error string.
+ */
+#ifndef RDFK_H
+#define RDFK_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDFK_VERSION 100
+
+#define RDFK_OK 0
+#define RDFK_EINVAL -1    /* bad argument                                   */
+#define RDFK_ECUDA -2     /* a CUDA runtime call failed (see last_error)    */
+#define RDFK_EWORKSPACE -3 /* workspace too small / misaligned              */
+#define RDFK_EARCH -4     /* device is not sm_100                           */
+
+/* box kinds: what MDAnalysis.lib.util.check_box returns for ts.dimensions   */
+#define RDFK_BOX_NONE 0  /* box=None: plain distances                        */
+#define RDFK_BOX_ORTHO 1 /* box[f][0..2] = lx,ly,lz (float32)                */
+#define RDFK_BOX_TRI 2   /* box[f][0..8] = float32 triclinic_vectors, row-major */
+
+int rdfk_version(void);
+const char *rdfk_last_error(void);
+
+/* sm count, compute capability and opt-in shared memory of `device`.       */
+int rdfk_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
+                     size_t *smem_optin_bytes);
+
+/* ------------------------------------------------------------------------
+ * InterRDF block kernel.  Replaces, for F frames at once,
+ *   capped_distance(g1.positions, g2.positions, range[1], box) + optional
+ *   exclusion_block mask + np.histogram(dist, bins=nbins, range=(r0, r1))
+ * (pmda/rdf.py:120-137) and the `res += r` of _reduce (pmda/rdf.py:180-190):
+ * counts are ADDED into hist[0..nbins).
+ *
+ *   xyz        [F][natoms][3] float32  trajectory frames (ts.positions)
+ *   idx1/idx2  [n1] / [n2] int32       AtomGroup.indices (NULL = 0..n-1)
+ *   same_group non-zero when idx1 and idx2 are the same selection (enables
+ *              the symmetric half-matrix schedule; counts are unchanged)
+ *   boxkind    RDFK_BOX_*, uniform over the call
+ *   box        [F][9] float32 (see RDFK_BOX_*), ignored for RDFK_BOX_NONE
+ *   r0, r1     histogram range; r1 is also capped_distance's max_cutoff
+ *   edges      [nbins+1] float64 = np.histogram([-1], nbins, (r0,r1))[1]
+ *   excl_a/b   exclusion_block (0,0 = None): pairs with i/excl_a == j/excl_b
+ *              are dropped (i, j are positions inside g1, g2)
+ *   hist       [nbins] uint64, accumulated into
+ * ------------------------------------------------------------------------ */
+size_t rdfk_rdf_workspace_bytes(int F, int n1, int n2, int nbins,
+                                int same_group);
+
+int rdfk_rdf_hist(const float *xyz, int F, int natoms, const int *idx1, int n1,
+                  const int *idx2, int n2, int same_group, int boxkind,
+                  const float *box, double r0, double r1, int nbins,
+                  const double *edges, int excl_a, int excl_b,
+                  unsigned long long *hist, void *workspace,
+                  size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * InterRDF_s block kernel (pmda/rdf.py:292-309 + _reduce :362-372), batched
+ * over F frames and n_sites site pairs in one launch.  For site pair s with
+ * groups A_s (n1_s atoms) and B_s (n2_s atoms), cell (a, b) of the dense
+ * tensor count[cell_off[s] + a*n2_s + b][0..nbins) receives +1 in the bin of
+ * the distance A_s[a]..B_s[b] for every frame in which that distance is
+ * within [r0, r1] (the per-pair one-hot np.histogram of :303-305).
+ *
+ *   idxA/idxB  concatenated AtomGroup.indices of all A_s / B_s
+ *   offA/offB  [n_sites+1] CSR offsets into idxA / idxB
+ *   cell_off   [n_sites+1] int64 prefix sums of n1_s*n2_s
+ *   count      [cell_off[n_sites]][nbins] uint32, accumulated into
+ * ------------------------------------------------------------------------ */
+int rdfk_rdf_sites(const float *xyz, int F, int natoms, const int *idxA,
+                   const int *idxB, const int *offA, const int *offB,
+                   const long long *cell_off, int n_sites,
+                   long long total_cells, int boxkind, const float *box,
+                   double r0, double r1, int nbins, const double *edges,
+                   unsigned int *count, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Diagnostics / measurement helpers (not on the reference path).
+ * ------------------------------------------------------------------------ */
+
+/* counters of the last rdfk_rdf_hist call that used `workspace`:
+ * out_host[0] = pairs sent to the fp64 re-check, out_host[1] = frames that
+ * ran entirely on the fp64 path, out_host[2] = tile work items executed,
+ * out_host[3] = pairs evaluated by the fp32 tile kernel.
+ * Synchronises `stream`.                                                    */
+int rdfk_rdf_stats(const void *workspace, unsigned long long *out_host,
+                   void *stream);
+
+/* FP32 roofline denominator: runs a dependent-chain-free FFMA kernel on every
+ * SM and returns the achieved TFLOP/s (2 flop per FFMA lane).  Synchronises. */
+int rdfk_measure_fp32_peak(double *tflops_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDFK_H */

@@ -1,0 +1,11 @@
+"""pmda_b200 -- B200-native drop-in for pmda's InterRDF / InterRDF_s hot path.
+
+    from pmda_b200.rdf import InterRDF, InterRDF_s
+    from pmda_b200.universe import Universe        # in-memory trajectories
+
+See DESIGN.md for the path, its boundary and the kernels; INTEGRATION.md for
+how pmda itself would bind the C ABI in include/rdfk.h.
+"""
+__version__ = "0.1.0"
+
+__all__ = ["rdf", "parallel", "util", "universe", "engine", "mdamath"]

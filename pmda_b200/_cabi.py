@@ -1,0 +1,130 @@
+"""ctypes binding of librdfk.so (include/rdfk.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call
+fails, an exception is raised.  torch is used only for device memory and
+streams (``tensor.data_ptr()``, ``torch.cuda.current_stream().cuda_stream``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librdfk.so")
+
+BOX_NONE, BOX_ORTHO, BOX_TRI = 0, 1, 2
+
+_lib = None
+
+
+class RdfkError(RuntimeError):
+    pass
+
+
+def _declare(L):
+    c_int, c_void_p, c_double = ctypes.c_int, ctypes.c_void_p, ctypes.c_double
+    c_size_t, c_ll = ctypes.c_size_t, ctypes.c_longlong
+    L.rdfk_version.restype = c_int
+    L.rdfk_version.argtypes = []
+    L.rdfk_last_error.restype = ctypes.c_char_p
+    L.rdfk_last_error.argtypes = []
+    L.rdfk_device_info.restype = c_int
+    L.rdfk_device_info.argtypes = [c_int, ctypes.POINTER(c_int),
+                                   ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                   ctypes.POINTER(c_size_t)]
+    L.rdfk_rdf_workspace_bytes.restype = c_size_t
+    L.rdfk_rdf_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    L.rdfk_rdf_hist.restype = c_int
+    L.rdfk_rdf_hist.argtypes = [
+        c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+        c_void_p, c_double, c_double, c_int, c_void_p, c_int, c_int, c_void_p,
+        c_void_p, c_size_t, c_void_p]
+    L.rdfk_rdf_sites.restype = c_int
+    L.rdfk_rdf_sites.argtypes = [
+        c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+        c_void_p, c_int, c_ll, c_int, c_void_p, c_double, c_double, c_int,
+        c_void_p, c_void_p, c_void_p]
+    L.rdfk_rdf_stats.restype = c_int
+    L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
+                                 c_void_p]
+    L.rdfk_measure_fp32_peak.restype = c_int
+    L.rdfk_measure_fp32_peak.argtypes = [ctypes.POINTER(c_double), c_void_p]
+
+
+#: every symbol include/rdfk.h declares
+EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_device_info",
+           "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
+           "rdfk_rdf_stats", "rdfk_measure_fp32_peak")
+
+
+def lib():
+    """Load librdfk.so; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RdfkError(
+                "CUDA extension %s is missing: run `python -m "
+                "pmda_b200.csrc.build` (there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().rdfk_last_error().decode("utf-8", "replace")
+        raise RdfkError("librdfk error %d: %s" % (rc, msg))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def device_info(device=0):
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    smem = ctypes.c_size_t()
+    check(lib().rdfk_device_info(int(device), ctypes.byref(sm),
+                                 ctypes.byref(maj), ctypes.byref(mnr),
+                                 ctypes.byref(smem)))
+    return {"sm_count": sm.value, "cc": (maj.value, mnr.value),
+            "smem_optin": smem.value}
+
+
+def rdf_workspace_bytes(F, n1, n2, nbins, same_group):
+    return int(lib().rdfk_rdf_workspace_bytes(int(F), int(n1), int(n2),
+                                              int(nbins), int(bool(same_group))))
+
+
+def rdf_hist(xyz, F, natoms, idx1, n1, idx2, n2, same_group, boxkind, box, r0,
+             r1, nbins, edges, excl, hist, workspace, stream):
+    """All tensor arguments are torch CUDA tensors (or None); see rdfk.h."""
+    xa, xb = (0, 0) if excl is None else (int(excl[0]), int(excl[1]))
+    check(lib().rdfk_rdf_hist(
+        _ptr(xyz), int(F), int(natoms), _ptr(idx1), int(n1), _ptr(idx2),
+        int(n2), int(bool(same_group)), int(boxkind), _ptr(box), float(r0),
+        float(r1), int(nbins), _ptr(edges), xa, xb, _ptr(hist),
+        _ptr(workspace), int(workspace.numel() * workspace.element_size()),
+        ctypes.c_void_p(int(stream))))
+
+
+def rdf_sites(xyz, F, natoms, idx_a, idx_b, off_a, off_b, cell_off, n_sites,
+              total_cells, boxkind, box, r0, r1, nbins, edges, count, stream):
+    check(lib().rdfk_rdf_sites(
+        _ptr(xyz), int(F), int(natoms), _ptr(idx_a), _ptr(idx_b), _ptr(off_a),
+        _ptr(off_b), _ptr(cell_off), int(n_sites), int(total_cells),
+        int(boxkind), _ptr(box), float(r0), float(r1), int(nbins), _ptr(edges),
+        _ptr(count), ctypes.c_void_p(int(stream))))
+
+
+def rdf_stats(workspace, stream):
+    out = (ctypes.c_ulonglong * 4)()
+    check(lib().rdfk_rdf_stats(_ptr(workspace), out,
+                               ctypes.c_void_p(int(stream))))
+    return {"slow_pairs": int(out[0]), "all_slow_frames": int(out[1]),
+            "tile_items": int(out[2]), "tile_pairs": int(out[3])}
+
+
+def measure_fp32_peak(stream=0):
+    v = ctypes.c_double()
+    check(lib().rdfk_measure_fp32_peak(ctypes.byref(v),
+                                       ctypes.c_void_p(int(stream))))
+    return float(v.value)

@@ -1,0 +1,688 @@
+"""Per-GPU frame-block streams: what replaces pmda's dask task graph
+(pmda/parallel.py:376-392) for the RDF analyses.
+
+For every block of frames that ``make_balanced_slices`` produced, the engine
+
+  1. cuts the block into batches of frames,
+  2. stages each batch host -> pinned -> device on a copy stream (or takes it
+     from the device-resident frame cache),
+  3. launches the C-ABI block kernel (``rdfk_rdf_hist`` / ``rdfk_rdf_sites``)
+     on the compute stream, accumulating into that block's device histogram,
+  4. at the end reads all block histograms back with one D2H copy.
+
+Frames are sharded over the local GPUs (``n_jobs``) and, under
+``torch.distributed``, over ranks; partial int64 histograms are combined with a
+single all-reduce.  Integer sums are order independent, so counts are
+bit-identical for any GPU count; the float64 per-frame volumes are summed on
+the host in frame order, like ``_reduce`` does in the reference.
+
+There is no CPU fallback: without the CUDA library / a GPU this raises.
+"""
+import os
+import threading
+import time
+import weakref
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _cabi, mdamath
+from .util import make_balanced_slices
+
+
+class Config(object):
+    #: raw frame bytes staged per batch (bigger = fewer launches)
+    batch_bytes = int(os.environ.get("PMDA_B200_BATCH_BYTES", 128 << 20))
+    #: never more frames than this per kernel call
+    max_batch_frames = int(os.environ.get("PMDA_B200_MAX_BATCH_FRAMES", 2048))
+    #: device-resident frame cache budget per GPU (0 disables the cache)
+    cache_bytes = int(os.environ.get("PMDA_B200_CACHE_BYTES", 48 << 30))
+    #: page-lock in-memory trajectories so H2D runs straight from them
+    pin_host = os.environ.get("PMDA_B200_PIN_HOST", "1") != "0"
+
+
+# --------------------------------------------------------------------------
+# backends.  The product backend is CUDA; tests may install a stand-in to
+# exercise the sharding logic on a CPU-only machine.
+# --------------------------------------------------------------------------
+class CudaBackend(object):
+    name = "cuda"
+
+    def devices(self, n_jobs):
+        if not torch.cuda.is_available():
+            raise _cabi.RdfkError(
+                "pmda_b200 needs a CUDA device (sm_100a): there is no CPU "
+                "fallback for InterRDF / InterRDF_s")
+        _cabi.lib()
+        if _dist_world() > 1:
+            return [torch.device("cuda", torch.cuda.current_device())]
+        n = max(1, min(int(n_jobs), torch.cuda.device_count()))
+        first = torch.cuda.current_device()
+        return [torch.device("cuda", (first + k) % torch.cuda.device_count())
+                for k in range(n)]
+
+    rdf_workspace_bytes = staticmethod(_cabi.rdf_workspace_bytes)
+    rdf_hist = staticmethod(_cabi.rdf_hist)
+    rdf_sites = staticmethod(_cabi.rdf_sites)
+
+
+_backend = CudaBackend()
+
+
+def _set_test_backend(backend):
+    """Test hook (tests/ only): swap the kernel backend; ``None`` restores CUDA."""
+    global _backend
+    _backend = CudaBackend() if backend is None else backend
+
+
+def _dist_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and \
+        dist.is_initialized() else 1
+
+
+def _dist_rank():
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() \
+        else 0
+
+
+# --------------------------------------------------------------------------
+# per-device state: streams, staging buffers, workspace, frame cache
+# --------------------------------------------------------------------------
+class _DeviceState(object):
+    def __init__(self, device):
+        self.device = device
+        self.is_cuda = device.type == "cuda"
+        self.lock = threading.Lock()
+        self.workspace = None
+        self.pinned = [None, None]
+        self.staged = [None, None]
+        self.cache = OrderedDict()   # key -> (xyz_dev, nbytes)
+        self.cache_used = 0
+        if self.is_cuda:
+            with torch.cuda.device(device):
+                self.copy_stream = torch.cuda.Stream(device)
+                self.compute_stream = torch.cuda.Stream(device)
+        else:
+            self.copy_stream = self.compute_stream = None
+
+    def get_workspace(self, nbytes):
+        if self.workspace is None or self.workspace.numel() < nbytes:
+            self.workspace = None
+            self.workspace = torch.empty(int(nbytes) + 256, dtype=torch.uint8,
+                                         device=self.device)
+        ws = self.workspace
+        off = (-ws.data_ptr()) % 256
+        return ws[off:off + nbytes]
+
+
+_states = {}
+_states_lock = threading.Lock()
+
+
+def _state(device):
+    key = (device.type, device.index)
+    with _states_lock:
+        st = _states.get(key)
+        if st is None:
+            st = _states[key] = _DeviceState(device)
+        return st
+
+
+def clear_cache():
+    """Drop every device-resident frame block (and the staging buffers)."""
+    with _states_lock:
+        for st in _states.values():
+            st.cache.clear()
+            st.cache_used = 0
+
+
+_pinned_arrays = {}
+
+
+def _maybe_pin(arr):
+    """cudaHostRegister a trajectory array once so copies from it are async."""
+    if not Config.pin_host or not torch.cuda.is_available():
+        return
+    base = arr
+    while isinstance(getattr(base, "base", None), np.ndarray):
+        base = base.base
+    key = base.__array_interface__["data"][0]
+    if key in _pinned_arrays or base.nbytes < (1 << 20):
+        return
+    try:
+        rc = torch.cuda.cudart().cudaHostRegister(key, base.nbytes, 0)
+        ok = int(rc) == 0
+    except Exception:       # registration is an optimisation only
+        ok = False
+    _pinned_arrays[key] = ok
+    if ok:
+        weakref.finalize(base, _unpin, key)
+
+
+def _unpin(key):
+    _pinned_arrays.pop(key, None)
+    try:
+        torch.cuda.cudart().cudaHostUnregister(key)
+    except Exception:
+        pass
+
+
+# --------------------------------------------------------------------------
+# trajectory access
+# --------------------------------------------------------------------------
+def _read_frames(traj, frames):
+    """-> (positions float32 [B,N,3], dimensions float32 [B,6] | None)"""
+    fb = getattr(traj, "frame_block", None)
+    if fb is not None:
+        return fb(frames)
+    pos, dims = [], []
+    for i in frames:                      # any MDAnalysis-like reader
+        ts = traj[i]
+        pos.append(np.array(ts.positions, dtype=np.float32, copy=True))
+        d = getattr(ts, "dimensions", None)
+        dims.append(None if d is None else np.array(d, dtype=np.float32))
+    pos = np.stack(pos) if pos else np.zeros((0, 0, 3), np.float32)
+    if any(d is None for d in dims):
+        return pos, None
+    return pos, np.stack(dims)
+
+
+def _box_rows(dims, n):
+    """per-frame (kind, box9, volume) with one host evaluation per distinct box"""
+    kinds = np.zeros(n, dtype=np.int32)
+    box9 = np.zeros((n, 9), dtype=np.float32)
+    vols = np.zeros(n, dtype=np.float64)
+    if dims is None:
+        return kinds, box9, vols
+    uniq, inv = np.unique(np.ascontiguousarray(dims), axis=0,
+                          return_inverse=True)
+    inv = inv.reshape(-1)
+    for u, row in enumerate(uniq):
+        kind, b = mdamath.classify_box(row)
+        vol = float(mdamath.box_volume(row)) if kind != _cabi.BOX_NONE else 0.0
+        sel = inv == u
+        kinds[sel] = kind
+        box9[sel] = b
+        vols[sel] = vol
+    return kinds, box9, vols
+
+
+def _runs(kinds):
+    """consecutive runs of equal box kind -> [(kind, lo, hi)]"""
+    out, lo = [], 0
+    for i in range(1, len(kinds) + 1):
+        if i == len(kinds) or kinds[i] != kinds[lo]:
+            out.append((int(kinds[lo]), lo, i))
+            lo = i
+    return out
+
+
+def _frame_shards(blocks, n_parts):
+    """Shard the concatenated frame list of all blocks into ``n_parts``
+    contiguous, balanced pieces (same rule as the block partition).  Returns
+    for every part a list of (block_id, position_in_run, frames: range)."""
+    sizes = [len(b) for b in blocks]
+    total = sum(sizes)
+    parts = [[] for _ in range(n_parts)]
+    if total == 0:
+        return parts
+    n_used = min(n_parts, total)
+    cuts = make_balanced_slices(total, n_used)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    for p, sl in enumerate(cuts):
+        lo = sl.start
+        hi = total if sl.stop is None else sl.stop
+        for b, blk in enumerate(blocks):
+            a, z = max(lo, starts[b]), min(hi, starts[b + 1])
+            if a < z:
+                sub = blk[int(a - starts[b]):int(z - starts[b])]
+                parts[p].append((b, int(a), sub))
+    return parts
+
+
+# --------------------------------------------------------------------------
+# the staging pipeline of one device
+# --------------------------------------------------------------------------
+class _Pipeline(object):
+    """Feeds frame batches of one trajectory to one device, double buffered."""
+
+    def __init__(self, st, traj, natoms):
+        self.st, self.traj, self.natoms = st, traj, natoms
+        self.frame_bytes = natoms * 12
+        nb = max(1, Config.batch_bytes // max(1, self.frame_bytes))
+        self.batch_frames = int(min(nb, Config.max_batch_frames))
+        self.dslot = 0
+        self.pslot = 0
+        self.h2d_done = [None, None]
+        self.compute_done = [None, None]
+        self.traj_key = id(traj)
+
+    def batches(self, frames):
+        for lo in range(0, len(frames), self.batch_frames):
+            yield frames[lo:lo + self.batch_frames]
+
+    def fetch(self, frames):
+        """-> (xyz_dev [B,N,3], dims_host, io_seconds, device slot or None)"""
+        st = self.st
+        t0 = time.time()
+        key = (self.traj_key, frames.start, frames.stop, frames.step)
+        hit = st.cache.get(key)
+        if hit is not None:
+            st.cache.move_to_end(key)
+            xyz_dev, dims, _ = hit
+            return xyz_dev, dims, time.time() - t0, None
+        pos, dims = _read_frames(self.traj, frames)
+        B = len(frames)
+        if pos.shape[1:] != (self.natoms, 3):
+            raise ValueError("trajectory frame has %r atoms, expected %d"
+                             % (pos.shape[1:], self.natoms))
+        nbytes = B * self.frame_bytes
+        if not st.is_cuda:
+            xyz_dev = torch.from_numpy(np.ascontiguousarray(pos))
+            return xyz_dev, dims, time.time() - t0, None
+        cap = self.batch_frames
+        shape = (cap, self.natoms, 3)
+        cacheable = Config.cache_bytes > 0 and \
+            st.cache_used + nbytes <= Config.cache_bytes
+        slot = None
+        with torch.cuda.device(st.device):
+            # destination: a cache entry of its own, or a rotating buffer
+            if cacheable:
+                xyz_dev = torch.empty((B, self.natoms, 3), dtype=torch.float32,
+                                      device=st.device)
+            else:
+                slot = self.dslot
+                self.dslot ^= 1
+                if st.staged[slot] is None or st.staged[slot].shape != shape:
+                    st.staged[slot] = None
+                    st.staged[slot] = torch.empty(shape, dtype=torch.float32,
+                                                  device=st.device)
+                if self.compute_done[slot] is not None:
+                    st.copy_stream.wait_event(self.compute_done[slot])
+                xyz_dev = st.staged[slot][:B]
+            # source: the trajectory array itself when it is page-locked,
+            # otherwise a rotating pinned staging buffer
+            src = None
+            if pos.flags.c_contiguous:
+                _maybe_pin(pos)
+                cand = torch.from_numpy(pos)
+                if cand.is_pinned():
+                    src = cand
+            if src is None:
+                ps = self.pslot
+                self.pslot ^= 1
+                if st.pinned[ps] is None or st.pinned[ps].shape != shape:
+                    st.pinned[ps] = torch.empty(shape, dtype=torch.float32,
+                                                pin_memory=True)
+                if self.h2d_done[ps] is not None:
+                    self.h2d_done[ps].synchronize()
+                np.copyto(st.pinned[ps][:B].numpy(), pos)
+                src = st.pinned[ps][:B]
+            else:
+                ps = None
+            with torch.cuda.stream(st.copy_stream):
+                xyz_dev.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st.copy_stream)
+            if ps is not None:
+                self.h2d_done[ps] = ev
+            st.compute_stream.wait_event(ev)
+        if cacheable:
+            dims_c = None if dims is None else np.array(dims, copy=True)
+            st.cache[key] = (xyz_dev, dims_c, nbytes)
+            st.cache_used += nbytes
+        return xyz_dev, dims, time.time() - t0, slot
+
+    def mark_compute_done(self, slot):
+        if slot is None or not self.st.is_cuda:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.st.compute_stream)
+        self.compute_done[slot] = ev
+
+
+class _Timer(object):
+    """CUDA-event timing of one batch on the compute stream."""
+
+    def __init__(self, st):
+        self.st = st
+        if st.is_cuda:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+        else:
+            self.t0 = self.t1 = 0.0
+
+    def start(self):
+        if self.st.is_cuda:
+            self.e0.record(self.st.compute_stream)
+        else:
+            self.t0 = time.time()
+
+    def stop(self):
+        if self.st.is_cuda:
+            self.e1.record(self.st.compute_stream)
+        else:
+            self.t1 = time.time()
+
+    def seconds(self):
+        if self.st.is_cuda:
+            self.e1.synchronize()
+            return self.e0.elapsed_time(self.e1) * 1e-3
+        return self.t1 - self.t0
+
+
+# --------------------------------------------------------------------------
+# public entry points
+# --------------------------------------------------------------------------
+def _to_dev_i32(idx, device):
+    return torch.as_tensor(np.asarray(idx, dtype=np.int32), device=device)
+
+
+def _as_u64_ptr_tensor(t):
+    return t  # int64 storage, the kernels treat it as uint64
+
+
+def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
+                  same_group, nbins, rng, edges, excl):
+    """All frames of one local device.  -> dict of partial results"""
+    st = _state(device)
+    be = _backend
+    out = {
+        "hist": None,
+        "vol": np.zeros(n_frames, dtype=np.float64),
+        "io": np.zeros(n_frames, dtype=np.float64),
+        "compute": np.zeros(n_frames, dtype=np.float64),
+        "first_launch": np.full(n_blocks, np.inf),
+    }
+    with st.lock:
+        cuda = st.is_cuda
+        ctx = torch.cuda.device(device) if cuda else _nullctx()
+        with ctx:
+            hist = torch.zeros((n_blocks, nbins), dtype=torch.int64,
+                               device=device)
+            edges_d = torch.as_tensor(edges, dtype=torch.float64,
+                                      device=device)
+            i1 = _to_dev_i32(idx1, device)
+            i2 = i1 if same_group else _to_dev_i32(idx2, device)
+            n1, n2 = len(idx1), len(idx2)
+            pipe = _Pipeline(st, traj, natoms)
+            ws = st.get_workspace(be.rdf_workspace_bytes(
+                pipe.batch_frames, n1, n2, nbins, same_group))
+            timers = []
+            if cuda:
+                # the zero-fill / uploads above ran on the current stream
+                st.compute_stream.wait_stream(torch.cuda.current_stream(device))
+            for (b, pos0, frames) in segs:
+                done = 0
+                for batch in pipe.batches(frames):
+                    B = len(batch)
+                    xyz, dims, t_io, slot = pipe.fetch(batch)
+                    kinds, box9, vols = _box_rows(dims, B)
+                    lo_f = pos0 + done
+                    out["vol"][lo_f:lo_f + B] = vols
+                    out["io"][lo_f:lo_f + B] = t_io / B
+                    box_d = torch.as_tensor(box9, device=device)
+                    if cuda:
+                        st.compute_stream.wait_stream(
+                            torch.cuda.current_stream(device))
+                    out["first_launch"][b] = min(out["first_launch"][b],
+                                                 time.time())
+                    tm = _Timer(st)
+                    tm.start()
+                    stream = st.compute_stream.cuda_stream if cuda else 0
+                    for kind, lo, hi in _runs(kinds):
+                        be.rdf_hist(xyz[lo:hi], hi - lo, natoms, i1, n1, i2,
+                                    n2, same_group, kind, box_d[lo:hi],
+                                    rng[0], rng[1], nbins, edges_d, excl,
+                                    hist[b], ws, stream)
+                    tm.stop()
+                    pipe.mark_compute_done(slot)
+                    timers.append((tm, lo_f, B))
+                    done += B
+            for tm, lo_f, B in timers:
+                out["compute"][lo_f:lo_f + B] = tm.seconds() / B
+            if cuda:
+                st.compute_stream.synchronize()
+            out["hist"] = hist
+    return out
+
+
+class _nullctx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def _combine(parts, device0, n_blocks, width, dtype):
+    """sum partial [n_blocks, width] tensors of the local devices on device0"""
+    total = None
+    for p in parts:
+        h = p["hist"].to(device0)
+        total = h if total is None else total + h
+    if total is None:
+        total = torch.zeros((n_blocks, width), dtype=dtype, device=device0)
+    return total
+
+
+def _allreduce(t):
+    import torch.distributed as dist
+    if _dist_world() > 1:
+        if t.is_cuda and dist.get_backend() == "gloo":
+            c = t.cpu()
+            dist.all_reduce(c)
+            t.copy_(c)
+        elif not t.is_cuda and dist.get_backend() == "nccl":
+            c = t.cuda()
+            dist.all_reduce(c)
+            t.copy_(c.cpu())
+        else:
+            dist.all_reduce(t)
+    return t
+
+
+def _run_parts(fn, devices, parts):
+    if len(devices) == 1:
+        return [fn(devices[0], parts[0])]
+    results = [None] * len(devices)
+    errors = []
+
+    def work(k):
+        try:
+            results[k] = fn(devices[k], parts[k])
+        except BaseException as exc:  # re-raised on the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(k,))
+               for k in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def _shard_for_this_rank(blocks, devices):
+    """frames -> ranks -> local devices; returns one segment list per device
+    and the number of frames in the run."""
+    world, rank = _dist_world(), _dist_rank()
+    n_frames = sum(len(b) for b in blocks)
+    mine = _frame_shards(blocks, world)[rank]
+    # second level: this rank's frames over its local devices
+    sub_blocks = [f for (_, _, f) in mine]
+    local = _frame_shards(sub_blocks, len(devices))
+    parts = []
+    for segs in local:
+        part = []
+        for (sb, pos_in_mine, frames) in segs:
+            b, pos0, parent = mine[sb]
+            off = sum(len(x) for x in sub_blocks[:sb])
+            part.append((b, pos0 + (pos_in_mine - off), frames))
+        parts.append(part)
+    return parts, n_frames
+
+
+def _finish(hist_np, vol, io, compute, first_launch, blocks, make_result):
+    """per-block tuples in the layout pmda/parallel.py:442-444 returns"""
+    res = []
+    pos = 0
+    for b, blk in enumerate(blocks):
+        n = len(blk)
+        v = 0.0
+        for x in vol[pos:pos + n]:       # sequential, like `res += r`
+            v = v + float(x)
+        t_io = io[pos:pos + n].copy()
+        t_c = compute[pos:pos + n].copy()
+        wait_end = first_launch[b] if np.isfinite(first_launch[b]) \
+            else time.time()
+        res.append((make_result(b, hist_np[b], np.float64(v)), t_io, t_c, 0.0,
+                    wait_end, np.sum(t_io), np.sum(t_c)))
+        pos += n
+    return res
+
+
+def run_rdf_blocks(traj, natoms, idx1, idx2, same_group, blocks, nbins, rng,
+                   edges, excl, n_jobs):
+    """InterRDF over frame blocks.  -> list of per-block tuples whose first
+    element is ``np.array([count int64[nbins], volume float64], dtype=object)``
+    (the accumulated ``_single_frame`` results of pmda/rdf.py:137 + :180-190).
+    """
+    devices = _backend.devices(n_jobs)
+    n_blocks = len(blocks)
+    parts, n_frames = _shard_for_this_rank(blocks, devices)
+
+    def fn(device, segs):
+        return _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames,
+                             idx1, idx2, same_group, nbins, rng, edges, excl)
+
+    outs = _run_parts(fn, devices, parts)
+    hist = _combine(outs, devices[0], n_blocks, nbins, torch.int64)
+    hist = _allreduce(hist)                      # the one NCCL all-reduce
+    extra = np.stack([sum(o["vol"] for o in outs),
+                      sum(o["io"] for o in outs),
+                      sum(o["compute"] for o in outs)])
+    if _dist_world() > 1:
+        extra = _allreduce(torch.from_numpy(extra)).numpy()
+    first = np.min(np.stack([o["first_launch"] for o in outs]), axis=0)
+    hist_np = hist.cpu().numpy()
+
+    def make_result(b, count, vol):
+        r = np.empty(2, dtype=object)
+        r[0] = count.astype(np.int64, copy=True)
+        r[1] = np.array(vol, dtype=np.float64)
+        return r
+
+    return _finish(hist_np, extra[0], extra[1], extra[2], first, blocks,
+                   make_result)
+
+
+def _run_sites_part(device, traj, natoms, segs, n_blocks, n_frames, site,
+                    nbins, rng, edges):
+    st = _state(device)
+    be = _backend
+    total_cells = int(site["cell_off"][-1])
+    out = {
+        "hist": None,
+        "vol": np.zeros(n_frames, dtype=np.float64),
+        "io": np.zeros(n_frames, dtype=np.float64),
+        "compute": np.zeros(n_frames, dtype=np.float64),
+        "first_launch": np.full(n_blocks, np.inf),
+    }
+    with st.lock:
+        cuda = st.is_cuda
+        ctx = torch.cuda.device(device) if cuda else _nullctx()
+        with ctx:
+            count = torch.zeros((n_blocks, total_cells * nbins),
+                                dtype=torch.int32, device=device)
+            edges_d = torch.as_tensor(edges, dtype=torch.float64,
+                                      device=device)
+            ia = _to_dev_i32(site["idx_a"], device)
+            ib = _to_dev_i32(site["idx_b"], device)
+            oa = _to_dev_i32(site["off_a"], device)
+            ob = _to_dev_i32(site["off_b"], device)
+            co = torch.as_tensor(np.asarray(site["cell_off"], dtype=np.int64),
+                                 device=device)
+            pipe = _Pipeline(st, traj, natoms)
+            timers = []
+            for (b, pos0, frames) in segs:
+                done = 0
+                for batch in pipe.batches(frames):
+                    B = len(batch)
+                    xyz, dims, t_io, slot = pipe.fetch(batch)
+                    kinds, box9, vols = _box_rows(dims, B)
+                    lo_f = pos0 + done
+                    out["vol"][lo_f:lo_f + B] = vols
+                    out["io"][lo_f:lo_f + B] = t_io / B
+                    box_d = torch.as_tensor(box9, device=device)
+                    if cuda:
+                        st.compute_stream.wait_stream(
+                            torch.cuda.current_stream(device))
+                    out["first_launch"][b] = min(out["first_launch"][b],
+                                                 time.time())
+                    tm = _Timer(st)
+                    tm.start()
+                    stream = st.compute_stream.cuda_stream if cuda else 0
+                    for kind, lo, hi in _runs(kinds):
+                        be.rdf_sites(xyz[lo:hi], hi - lo, natoms, ia, ib, oa,
+                                     ob, co, site["n_sites"], total_cells,
+                                     kind, box_d[lo:hi], rng[0], rng[1], nbins,
+                                     edges_d, count[b], stream)
+                    tm.stop()
+                    pipe.mark_compute_done(slot)
+                    timers.append((tm, lo_f, B))
+                    done += B
+            for tm, lo_f, B in timers:
+                out["compute"][lo_f:lo_f + B] = tm.seconds() / B
+            if cuda:
+                st.compute_stream.synchronize()
+            out["hist"] = count
+    return out
+
+
+def run_rdf_s_blocks(traj, natoms, site, blocks, nbins, rng, edges, n_jobs):
+    """InterRDF_s over frame blocks.  ``site`` holds the CSR description of
+    the site pairs (see rdf.InterRDF_s).  The first element of every block
+    tuple is ``np.array([<object array of n float64 [n1,n2,nbins]>, volume])``
+    like pmda/rdf.py:309 accumulated by :362-372."""
+    devices = _backend.devices(n_jobs)
+    n_blocks = len(blocks)
+    total_cells = int(site["cell_off"][-1])
+    parts, n_frames = _shard_for_this_rank(blocks, devices)
+
+    def fn(device, segs):
+        return _run_sites_part(device, traj, natoms, segs, n_blocks, n_frames,
+                               site, nbins, rng, edges)
+
+    outs = _run_parts(fn, devices, parts)
+    cnt = _combine(outs, devices[0], n_blocks, total_cells * nbins,
+                   torch.int32)
+    cnt = _allreduce(cnt)
+    extra = np.stack([sum(o["vol"] for o in outs),
+                      sum(o["io"] for o in outs),
+                      sum(o["compute"] for o in outs)])
+    if _dist_world() > 1:
+        extra = _allreduce(torch.from_numpy(extra)).numpy()
+    first = np.min(np.stack([o["first_launch"] for o in outs]), axis=0)
+    cnt_np = cnt.cpu().numpy()
+    cell_off = np.asarray(site["cell_off"], dtype=np.int64)
+    shapes = site["shapes"]
+
+    def make_result(b, flat, vol):
+        per_site = np.empty(len(shapes), dtype=object)
+        dense = flat.reshape(total_cells, nbins)
+        for s, (n1, n2) in enumerate(shapes):
+            per_site[s] = dense[cell_off[s]:cell_off[s + 1]].astype(
+                np.float64).reshape(n1, n2, nbins)
+        r = np.empty(2, dtype=object)
+        r[0] = per_site
+        r[1] = np.array(vol, dtype=np.float64)
+        return r
+
+    return _finish(cnt_np, extra[0], extra[1], extra[2], first, blocks,
+                   make_result)

@@ -1,0 +1,118 @@
+"""Synthetic trajectories for the BASELINE.json configurations.
+
+Everything is drawn from ``numpy.random.Generator(PCG64(seed))`` in float64,
+cast to float32 and kept strictly inside the primary cell (1e-4 fractional
+margin for triclinic boxes) so that every plausible pre-wrap of the reference
+is the identity (SURVEY.md 8c "residual risk").
+"""
+import numpy as np
+
+from . import mdamath
+from .universe import Universe
+
+BASE_SEED = 20261019
+
+
+def _rng(cfg, extra=0):
+    return np.random.Generator(np.random.PCG64(BASE_SEED + cfg + 1000 * extra))
+
+
+def _clamp_ortho(pos, lengths):
+    hi = np.nextafter(np.asarray(lengths, dtype=np.float32), np.float32(0))
+    return np.minimum(np.maximum(pos, np.float32(0)), hi)
+
+
+def uniform_ortho(n_frames, n_atoms, lengths, rng):
+    """ideal gas in an orthorhombic box -> float32 [F,N,3]"""
+    L = np.asarray(lengths, dtype=np.float64)
+    pos = (rng.random((n_frames, n_atoms, 3)) * L).astype(np.float32)
+    return _clamp_ortho(pos, L)
+
+
+def uniform_triclinic(n_frames, n_atoms, dimensions, rng, margin=1e-4):
+    """ideal gas inside a triclinic cell (fractional coords in
+    [margin, 1-margin]) -> float32 [F,N,3]"""
+    m = mdamath.triclinic_vectors(dimensions, dtype=np.float64)
+    frac = margin + (1.0 - 2.0 * margin) * rng.random((n_frames, n_atoms, 3))
+    return (frac @ m).astype(np.float32)
+
+
+def water_like(n_frames, n_atoms, L, rng, sigma=0.5):
+    """jittered simple-cubic lattice + per-frame Gaussian displacement"""
+    m = int(np.ceil(n_atoms ** (1.0 / 3.0)))
+    a = L / m
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"),
+                 axis=-1).reshape(-1, 3)
+    sites = (g[rng.permutation(len(g))[:n_atoms]] + 0.5) * a
+    pos = sites[None] + rng.normal(0.0, sigma, (n_frames, n_atoms, 3))
+    pos = np.mod(pos, L)
+    return _clamp_ortho(pos.astype(np.float32), [L, L, L])
+
+
+# -- the five BASELINE.json configurations ----------------------------------
+def config1(n_frames=100, n_atoms=3000, seed_extra=0):
+    """InterRDF O-O, 3,000-water box, cubic L=44.78, 75 bins, range 0-15"""
+    L = 44.78
+    rng = _rng(1, seed_extra)
+    pos = water_like(n_frames, n_atoms, L, rng)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    return u, dict(g1=u.atoms, g2=u.atoms, nbins=75, range=(0.0, 15.0))
+
+
+def config2(n_frames=1000, n_atoms=100_000, seed_extra=0):
+    """InterRDF all-atom, 100k atoms, cubic L=100, 200 bins, range 0-15"""
+    L = 100.0
+    rng = _rng(2, seed_extra)
+    pos = uniform_ortho(n_frames, n_atoms, [L, L, L], rng)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    return u, dict(g1=u.atoms, g2=u.atoms, nbins=200, range=(0.0, 15.0))
+
+
+def config3(n_frames=2000, n_atoms=50_000, n_sites=64, n_near=256,
+            seed_extra=0):
+    """InterRDF_s: 64 ion-water site pairs (1 ion x 256 nearest atoms of
+    frame 0) in a 50k-atom cubic box L=79.4, 75 bins, range 0-15"""
+    L = 79.4
+    rng = _rng(3, seed_extra)
+    base = uniform_ortho(1, n_atoms, [L, L, L], rng)[0].astype(np.float64)
+    pos = base[None] + rng.normal(0.0, 0.3, (n_frames, n_atoms, 3))
+    pos = _clamp_ortho(np.mod(pos, L).astype(np.float32), [L, L, L])
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    ions = rng.choice(n_atoms, n_sites, replace=False)
+    ags = []
+    p0 = pos[0].astype(np.float64)
+    for ion in ions:
+        d = p0 - p0[ion]
+        d -= L * np.round(d / L)
+        order = np.argsort(np.einsum("ij,ij->i", d, d))
+        near = np.sort(order[1:n_near + 1])
+        ags.append([u.atoms[[ion]], u.atoms[near]])
+    return u, dict(ags=ags, nbins=75, range=(0.0, 15.0), density=True)
+
+
+def config4(n_frames=5000, n_atoms=250_000, seed_extra=0):
+    """InterRDF, 250k atoms, rhombic-dodecahedron-like triclinic box"""
+    dims = [152.3, 152.3, 152.3, 60.0, 60.0, 90.0]
+    rng = _rng(4, seed_extra)
+    pos = uniform_triclinic(n_frames, n_atoms, dims, rng)
+    u = Universe(pos, dims)
+    return u, dict(g1=u.atoms, g2=u.atoms, nbins=75, range=(0.0, 15.0))
+
+
+def config5(n_frames=10_000, n_atoms=1_000_000, n_g1=1000, seed_extra=0):
+    """InterRDF 1k x 1M, membrane-like slab density, ortho 316.2x316.2x100"""
+    Ls = [316.2, 316.2, 100.0]
+    rng = _rng(5, seed_extra)
+    pos = uniform_ortho(n_frames, n_atoms, Ls, rng)
+    # half of the atoms sit in two Gaussian slabs (z = 35 / 65, sigma = 8)
+    n_slab = n_atoms // 2
+    centre = np.where(rng.random(n_slab) < 0.5, 35.0, 65.0)
+    z = centre[None] + rng.normal(0.0, 8.0, (n_frames, n_slab))
+    pos[:, :n_slab, 2] = np.mod(z, Ls[2]).astype(np.float32)
+    pos = _clamp_ortho(pos, Ls)
+    u = Universe(pos, Ls + [90, 90, 90])
+    g1 = u.atoms[np.sort(rng.choice(n_slab, n_g1, replace=False))]
+    return u, dict(g1=g1, g2=u.atoms, nbins=75, range=(0.0, 15.0))
+
+
+CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}

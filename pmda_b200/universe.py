@@ -1,0 +1,239 @@
+"""A small in-memory, duck-typed stand-in for the MDAnalysis objects the hot
+path touches.
+
+pmda only uses: ``universe.trajectory`` (``check_slice_indices``, ``[i] -> ts``,
+``.filename``, ``.ts``), ``ts.positions / .dimensions / .volume / .frame``,
+``universe.filename``, ``universe.dimensions``, ``universe.atoms[idx]``,
+``ag.indices / .positions / .universe / .n_atoms / len(ag)``
+(pmda/parallel.py:210-213, 351, 421-434; pmda/rdf.py:95-100, 121-126, 135).
+A real ``MDAnalysis.Universe`` offers the same attributes, so analyses accept
+either; nothing here imports MDAnalysis.
+"""
+import numbers
+
+import numpy as np
+
+from . import mdamath
+
+
+class Timestep(object):
+    """One coordinate frame: float32 positions [N,3], float32 dimensions [6]."""
+
+    def __init__(self, frame, positions, dimensions):
+        self.frame = int(frame)
+        self.positions = positions
+        self.dimensions = dimensions
+
+    @property
+    def n_atoms(self):
+        return len(self.positions)
+
+    @property
+    def volume(self):
+        """unit-cell volume (0 without a box), like ``Timestep.volume``"""
+        if self.dimensions is None:
+            return 0.0
+        return float(mdamath.box_volume(self.dimensions))
+
+
+class MemoryTrajectory(object):
+    """Frames held as one contiguous float32 array ``[F, N, 3]`` plus per-frame
+    ``dimensions`` ``[F, 6]`` (or ``None`` for no periodic box)."""
+
+    def __init__(self, positions, dimensions=None, filename=None):
+        pos = np.asarray(positions, dtype=np.float32)
+        if pos.ndim == 2:
+            pos = pos[None]
+        if pos.ndim != 3 or pos.shape[2] != 3:
+            raise ValueError("positions must have shape [n_frames, n_atoms, 3]")
+        self.positions = np.ascontiguousarray(pos)
+        n_frames = self.positions.shape[0]
+        if dimensions is None:
+            self.dimensions = None
+        else:
+            dims = np.asarray(dimensions, dtype=np.float32)
+            if dims.ndim == 1:
+                dims = np.broadcast_to(dims, (n_frames, 6))
+            if dims.shape != (n_frames, 6):
+                raise ValueError("dimensions must have shape [6] or "
+                                 "[n_frames, 6]")
+            self.dimensions = np.ascontiguousarray(dims)
+        self.filename = filename
+        self.ts = None
+        if n_frames:
+            self[0]
+
+    @property
+    def n_frames(self):
+        return self.positions.shape[0]
+
+    @property
+    def n_atoms(self):
+        return self.positions.shape[1]
+
+    def __len__(self):
+        return self.n_frames
+
+    def _read(self, i):
+        dims = None if self.dimensions is None else self.dimensions[i]
+        self.ts = Timestep(i, self.positions[i], dims)
+        return self.ts
+
+    def __getitem__(self, item):
+        if isinstance(item, numbers.Integral):
+            i = int(item)
+            if i < 0:
+                i += self.n_frames
+            if not 0 <= i < self.n_frames:
+                raise IndexError("Index {} exceeds length of trajectory ({})."
+                                 .format(item, self.n_frames))
+            return self._read(i)
+        if isinstance(item, slice):
+            return (self._read(i) for i in range(*item.indices(self.n_frames)))
+        raise TypeError("Trajectories must be an indexed using an integer or "
+                        "slice")
+
+    def __iter__(self):
+        for i in range(self.n_frames):
+            yield self._read(i)
+
+    def check_slice_indices(self, start, stop, step):
+        """Resolve (start, stop, step) against the trajectory length the way
+        ``ProtoReader.check_slice_indices`` does (call site
+        pmda/parallel.py:351-352)."""
+        for name, var in (("start", start), ("stop", stop), ("step", step)):
+            if var is not None and not isinstance(var, numbers.Integral):
+                raise TypeError("{0} is not an integer".format(name))
+        n = len(self)
+        step = 1 if step is None else int(step)
+        if step == 0:
+            raise ValueError("Step size is zero")
+        if start is None:
+            start = 0 if step > 0 else n - 1
+        else:
+            start = int(start)
+            if start < 0:
+                start += n
+            if start < 0:
+                start = 0
+        if step < 0 and start >= n:
+            start = n - 1
+        if stop is None:
+            stop = n if step > 0 else -1
+        else:
+            stop = int(stop)
+            if stop < 0:
+                stop += n
+        if step > 0 and stop > n:
+            stop = n
+        return start, stop, step
+
+    # -- fast path used by the frame stager (not part of the MDAnalysis API) --
+    def frame_block(self, frames):
+        """positions [B,N,3] and dimensions [B,6]|None for a range/list of
+        frame numbers, without touching ``self.ts``."""
+        if isinstance(frames, range) and len(frames) and frames.step > 0:
+            sl = slice(frames.start, frames.stop, frames.step)
+            pos = self.positions[sl]
+            dims = None if self.dimensions is None else self.dimensions[sl]
+        else:
+            ix = np.asarray(list(frames), dtype=np.intp)
+            pos = self.positions[ix]
+            dims = None if self.dimensions is None else self.dimensions[ix]
+        return pos, dims
+
+
+class AtomGroup(object):
+    """Ordered selection of atoms of one Universe."""
+
+    def __init__(self, universe, indices):
+        self.universe = universe
+        self.indices = np.asarray(indices, dtype=np.intp).reshape(-1)
+
+    @property
+    def n_atoms(self):
+        return len(self.indices)
+
+    def __len__(self):
+        return len(self.indices)
+
+    @property
+    def positions(self):
+        """float32 [n,3] copy of the current frame's coordinates"""
+        return self.universe.trajectory.ts.positions[self.indices]
+
+    def __getitem__(self, item):
+        if isinstance(item, numbers.Integral):
+            return AtomGroup(self.universe, [self.indices[item]])
+        return AtomGroup(self.universe, self.indices[item])
+
+    def __add__(self, other):
+        return AtomGroup(self.universe,
+                         np.concatenate([self.indices, other.indices]))
+
+    def select_atoms(self, sel):
+        return self.universe._select(sel, self.indices)
+
+
+class Universe(object):
+    """``Universe(positions, dimensions)`` -- in-memory system.
+
+    positions  : float32 [n_frames, n_atoms, 3]
+    dimensions : [6] or [n_frames, 6] ``lx, ly, lz, alpha, beta, gamma`` or None
+    names      : optional per-atom names for ``select_atoms('name A B')``
+    """
+
+    def __init__(self, positions, dimensions=None, names=None, filename=None,
+                 trajectory_filename=None):
+        self.trajectory = MemoryTrajectory(positions, dimensions,
+                                           filename=trajectory_filename)
+        self.filename = filename
+        n = self.trajectory.n_atoms
+        self.names = None if names is None else np.asarray(names)
+        if self.names is not None and len(self.names) != n:
+            raise ValueError("names must have one entry per atom")
+        self.atoms = AtomGroup(self, np.arange(n, dtype=np.intp))
+
+    @property
+    def dimensions(self):
+        return self.trajectory.ts.dimensions
+
+    def select_atoms(self, sel):
+        return self._select(sel, self.atoms.indices)
+
+    def _select(self, sel, within):
+        """Tiny selection language: ``all``, ``name A [B ...]``,
+        ``index i:j`` (half-open) or ``index i j k``."""
+        tok = sel.split()
+        if not tok or tok == ["all"]:
+            return AtomGroup(self, within)
+        if tok[0] == "name":
+            if self.names is None:
+                raise ValueError("this Universe has no atom names")
+            mask = np.isin(self.names[within], tok[1:])
+            return AtomGroup(self, within[mask])
+        if tok[0] == "index":
+            if len(tok) == 2 and ":" in tok[1]:
+                a, b = tok[1].split(":")
+                want = np.arange(int(a), int(b))
+            else:
+                want = np.asarray([int(t) for t in tok[1:]])
+            return AtomGroup(self, within[np.isin(within, want)])
+        raise ValueError("unsupported selection: %r" % sel)
+
+    # -- persistence of the synthetic systems (lossless float32 .npz) --------
+    def save(self, path):
+        kw = {"positions": self.trajectory.positions}
+        if self.trajectory.dimensions is not None:
+            kw["dimensions"] = self.trajectory.dimensions
+        if self.names is not None:
+            kw["names"] = self.names
+        np.savez(path, **kw)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path, allow_pickle=False)
+        return cls(z["positions"],
+                   z["dimensions"] if "dimensions" in z else None,
+                   z["names"] if "names" in z else None,
+                   filename=path, trajectory_filename=path)
