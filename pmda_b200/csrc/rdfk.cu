@@ -158,18 +158,28 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src,
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "MBAR_WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MBAR_WAIT_DONE;\n"
-      "bra MBAR_WAIT_LOOP;\n"
-      "MBAR_WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0u;
+}
+// The wait loop is written in C++ (not as branches inside the asm) so that the
+// compiler sees the divergence and re-converges the warp afterwards: with the
+// loop hidden in inline PTX, lanes leaving try_wait at different times stayed
+// split for the whole tile and every instruction issued twice (ncu: 16.8
+// active threads per instruction, profiles/r1_notes.md).
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -521,43 +531,79 @@ struct PairArgs {
   const float2 *tables;
   HistParams hp;
   int hist_copies;       // warp-private shared copies (0 = global atomics)
+  unsigned int flush_every;  // items between 32-bit shared-counter flushes
   unsigned long long *hist;
   WsHeader *header;
 };
 
+// ---------------------------------------------------------------------------
+// In-range pairs are a minority (0.1-16 % of evaluated pairs) scattered over
+// the lanes of a warp, so binning them where they are found wastes the warp on
+// divergence (measured: 2.8x slower, tools/ubench2.cu).  Instead every thread
+// appends its hits to a private queue in shared memory with three predicated
+// instructions (no branch), and the warp drains all queues at warp-uniform
+// points.  A queue entry is (fp32 r2, j-step); the i-atom is implied by the
+// owning thread.  The rare band failure recovers the exact (u, r) pair by
+// re-evaluating the 4*RI candidates of that j-step (resolve_band).
+// ---------------------------------------------------------------------------
+constexpr int QS = 16;                 // queue slots per thread
+constexpr int Q_STRIDE = TPB * 4;      // bytes between slots of one thread
+constexpr int Q_JOFF = QS * TPB * 4;   // byte offset of the j-step array
+constexpr int Q_CHECK = 2;             // drain check every Q_CHECK u-steps
+static_assert(QS >= 2 * Q_CHECK * RI, "queue must absorb one check interval");
+
+__device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut,
+                                       uint32_t jb) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.lt.f32 p, %1, %2;\n"
+      "@p st.shared.f32 [%0], %1;\n"
+      "@p st.shared.u32 [%0+%4], %3;\n"
+      "@p add.u32 %0, %0, %5;\n"
+      "}\n"
+      : "+r"(qaddr)
+      : "f"(r2), "f"(cut), "r"(jb), "n"(Q_JOFF), "n"(Q_STRIDE)
+      : "memory");
+}
+
+// Rare path: the `rank`-th (0-based, in (u, r) scan order) pair of j-step `jb`
+// whose fp32 r2 equals `r2` bit for bit; returns its exact bin (or -1).
 template <int BOXKIND>
-__device__ __forceinline__ void bin_pair(float r2, float xi, float yi, float zi,
-                                         float xj, float yj, float zj,
-                                         unsigned int w, float r2_low,
-                                         float inv_dr, float koff, int nbins,
-                                         const float2 *__restrict__ tab,
-                                         const FrameParams *fp,
-                                         const HistParams *hp,
-                                         unsigned int *wh,
-                                         unsigned long long *ghist,
-                                         unsigned int &n_slow) {
-  if (r2 < r2_low) return;
-  const float d = sqrt_approx(r2);
-  int k = __float2int_rd(__fmaf_rn(d, inv_dr, koff));
-  k = max(0, min(k, nbins - 1));
-  const float2 t = __ldg(tab + k);
-  if (!(r2 >= t.x && r2 < t.y)) {
-    k = exact_bin<BOXKIND>(xi, yi, zi, xj, yj, zj, fp, hp);
-    ++n_slow;
-    if (k < 0) return;
+__device__ __noinline__ int resolve_band(
+    float r2, uint32_t jb, int rank, const float *xs, float x0, float x1,
+    float x2, float x3, float y0, float y1, float y2, float y3, float z0,
+    float z1, float z2, float z3, const FrameParams *__restrict__ fp,
+    const HistParams *__restrict__ hp) {
+  const FastBox fb = load_fastbox(fp);
+  const float xi[4] = {x0, x1, x2, x3}, yi[4] = {y0, y1, y2, y3},
+              zi[4] = {z0, z1, z2, z3};
+  const float *ys = xs + TILE, *zs = xs + 2 * TILE;
+  int seen = 0;
+  for (int u = 0; u < 4; ++u) {
+    const float xj = xs[jb + u], yj = ys[jb + u], zj = zs[jb + u];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+      const float v = r2_fast<BOXKIND>(__fsub_rn(xj, xi[r]), __fsub_rn(yj, yi[r]),
+                                       __fsub_rn(zj, zi[r]), fb);
+      if (__float_as_uint(v) == __float_as_uint(r2)) {
+        if (seen == rank)
+          return exact_bin<BOXKIND>(xi[r], yi[r], zi[r], xj, yj, zj, fp, hp);
+        ++seen;
+      }
+    }
   }
-  if (wh)
-    atomicAdd(wh + k, w);
-  else
-    atomicAdd(ghist + k, (unsigned long long)w);
+  return -1;  // unreachable: the entry was produced by one of these pairs
 }
 
 template <int BOXKIND>
 __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
+  static_assert(RI == 4, "resolve_band takes four i-atoms");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *jbuf = reinterpret_cast<float *>(smem_raw);            // [2][3][TILE]
-  unsigned int *hist_s =
-      reinterpret_cast<unsigned int *>(smem_raw + 2 * 3 * TILE * sizeof(float));
+  float *q_r2 = jbuf + 2 * 3 * TILE;                            // [QS][TPB]
+  uint32_t *q_j = reinterpret_cast<uint32_t *>(q_r2 + QS * TPB);  // [QS][TPB]
+  unsigned int *hist_s = reinterpret_cast<unsigned int *>(q_j + QS * TPB);
   __shared__ uint64_t bars[2];
   __shared__ int s_next[2];
   __shared__ HistParams s_hp;
@@ -567,6 +613,8 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
   const int nbins = a.hp.nbins;
   const int copies = a.hist_copies;
   unsigned int *wh = copies ? hist_s + (size_t)(warp % copies) * nbins : nullptr;
+  const uint32_t qbase = smem_u32(q_r2 + tid);
+  uint32_t qaddr = qbase;
 
   for (int b = tid; b < copies * nbins; b += TPB) hist_s[b] = 0u;
   if (tid == 0) {
@@ -577,11 +625,9 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
   }
   __syncthreads();
 
-  auto issue_load = [&](int item, int buf) {
-    // thread 0 only: j-tile of `item` -> jbuf[buf]
-    const int f = item / a.items_per_frame;
+  auto decode = [&](int item, int &f, int &it, int &jt) {
+    f = item / a.items_per_frame;
     const int w = item - f * a.items_per_frame;
-    int it, jt;
     if (a.symmetric) {
       const int nt = a.nt1, B = (nt - 1) / 2 + 1;
       if (w < nt * B) { it = w / B; jt = it + (w - it * B); }
@@ -590,7 +636,11 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
     } else {
       it = w / a.nt2; jt = w - it * a.nt2;
     }
-    (void)it;
+  };
+  auto issue_load = [&](int item, int buf) {
+    // thread 0 only: j-tile of `item` -> jbuf[buf] by three 1-D TMA copies
+    int f, it, jt;
+    decode(item, f, it, jt);
     const float *src = a.g2 + (size_t)f * 3 * a.np2 + (size_t)jt * TILE;
     float *dst = jbuf + (size_t)buf * 3 * TILE;
     mbar_expect_tx(&bars[buf], 3u * TILE * sizeof(float));
@@ -610,7 +660,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
 
   unsigned int n_slow = 0;
   unsigned int n_items = 0;
-  uint32_t phase[2] = {0u, 0u};
+  uint32_t phase0 = 0u, phase1 = 0u;
   int buf = 0;
   int cur = s_next[0];
 
@@ -623,24 +673,13 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
       if (nxt < a.total_items) issue_load(nxt, buf ^ 1);
     }
 
-    // decode the current item
-    const int f = cur / a.items_per_frame;
-    const int w = cur - f * a.items_per_frame;
-    int it, jt;
-    if (a.symmetric) {
-      const int nt = a.nt1, B = (nt - 1) / 2 + 1;
-      if (w < nt * B) { it = w / B; jt = it + (w - it * B); }
-      else { it = w - nt * B; jt = it + nt / 2; }
-      if (jt >= nt) jt -= nt;
-    } else {
-      it = w / a.nt2; jt = w - it * a.nt2;
-    }
+    int f, it, jt;
+    decode(cur, f, it, jt);
     const unsigned int weight = (a.symmetric && it != jt) ? 2u : 1u;
     const FrameParams *fp = a.fparams + f;
     const float2 *tab = a.tables + (size_t)f * nbins;
     const FastBox fb = load_fastbox(fp);
-    const float r2_cut = fp->r2_cut, r2_low = fp->r2_low;
-    const float inv_dr = fp->inv_dr, koff = fp->koff;
+    const float r2_cut = fp->r2_cut;
     const int all_slow = fp->all_slow;
 
     // my i-atoms (coalesced; NaN in the padded tail)
@@ -659,8 +698,46 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
     const float *ys = xs + TILE;
     const float *zs = xs + 2 * TILE;
 
-    mbar_wait(&bars[buf], phase[buf]);
-    phase[buf] ^= 1u;
+    if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
+    else { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
+
+    // bin everything queued so far (warp-uniform call sites only).  The loop
+    // bound is warp-uniform (REDUX max) and the per-lane work is a structured
+    // `if`: a per-lane trip count left the lanes split into sub-warps for the
+    // rest of the tile (BSYNC did not merge them; ncu showed 16.8 active
+    // threads per instruction in the hot loop).
+    auto drain = [&]() {
+      const unsigned int n = (qaddr - qbase) / Q_STRIDE;
+      const unsigned int nmax = __reduce_max_sync(0xffffffffu, n);
+      const float r2_low = fp->r2_low, inv_dr = fp->inv_dr, koff = fp->koff;
+      for (unsigned int s = 0; s < nmax; ++s) {
+        if (s < n) {
+          const float r2 = q_r2[s * TPB + tid];
+          int k = __float2int_rd(__fmaf_rn(sqrt_approx(r2), inv_dr, koff));
+          k = max(0, min(k, nbins - 1));
+          const float2 t = __ldg(tab + k);
+          bool ok = r2 >= r2_low;
+          if (ok && !(r2 >= t.x && r2 < t.y)) {
+            const uint32_t jb = q_j[s * TPB + tid];
+            int rank = 0;
+            for (unsigned int e = 0; e < s; ++e)
+              rank += (q_j[e * TPB + tid] == jb &&
+                       __float_as_uint(q_r2[e * TPB + tid]) ==
+                           __float_as_uint(r2));
+            k = resolve_band<BOXKIND>(r2, jb, rank, xs, xi[0], xi[1], xi[2],
+                                      xi[3], yi[0], yi[1], yi[2], yi[3], zi[0],
+                                      zi[1], zi[2], zi[3], fp, &s_hp);
+            ++n_slow;
+            ok = k >= 0;
+          }
+          if (ok) {
+            if (wh) atomicAdd(wh + k, weight);
+            else atomicAdd(a.hist + k, (unsigned long long)weight);
+          }
+        }
+      }
+      qaddr = qbase;
+    };
 
     if (!all_slow) {
 #pragma unroll 1
@@ -673,23 +750,23 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
         const float zj4[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          float r2v[RI];
 #pragma unroll
-          for (int r = 0; r < RI; ++r)
-            r2v[r] = r2_fast<BOXKIND>(__fsub_rn(xj4[u], xi[r]),
-                                      __fsub_rn(yj4[u], yi[r]),
-                                      __fsub_rn(zj4[u], zi[r]), fb);
-          float m = fminf(fminf(r2v[0], r2v[1]), fminf(r2v[2], r2v[3]));
-          if (m < r2_cut) {
-#pragma unroll
-            for (int r = 0; r < RI; ++r)
-              if (r2v[r] < r2_cut)
-                bin_pair<BOXKIND>(r2v[r], xi[r], yi[r], zi[r], xj4[u], yj4[u],
-                                  zj4[u], weight, r2_low, inv_dr, koff, nbins,
-                                  tab, fp, &s_hp, wh, a.hist, n_slow);
+          for (int r = 0; r < RI; ++r) {
+            const float r2 = r2_fast<BOXKIND>(__fsub_rn(xj4[u], xi[r]),
+                                              __fsub_rn(yj4[u], yi[r]),
+                                              __fsub_rn(zj4[u], zi[r]), fb);
+            q_push(qaddr, r2, r2_cut, (uint32_t)j);
+          }
+          if ((u % Q_CHECK) == Q_CHECK - 1) {
+            // room for the next Q_CHECK*RI pushes in every lane?
+            if (__any_sync(0xffffffffu,
+                           qaddr > qbase + (QS - Q_CHECK * RI) * Q_STRIDE)) {
+              drain();
+            }
           }
         }
       }
+      drain();
     } else {
       // frame not provably safe for fp32: every pair through the fp64 path
       for (int j = 0; j < jcount; ++j) {
@@ -708,8 +785,8 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
       }
     }
     ++n_items;
-    // shared counters are 32-bit: a warp adds at most 32*RI*TILE*2 per item
-    if (copies && (n_items & 4095u) == 0u) {
+    // shared counters are 32-bit: flush long before they can wrap
+    if (copies && (n_items % a.flush_every) == 0u) {
       __syncthreads();
       for (int b = tid; b < nbins; b += TPB) {
         unsigned long long s = 0;
@@ -978,7 +1055,15 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   int copies = (int)(HIST_SMEM_BUDGET / per_copy);
   if (copies > NWARP) copies = NWARP;
   a.hist_copies = copies;
-  const size_t smem = 2 * 3 * TILE * sizeof(float) + (size_t)copies * per_copy;
+  {
+    // one item adds at most 32*RI*TILE*2 to a warp's copy; several warps may
+    // share a copy when nbins is large
+    const unsigned int sharers = copies ? (NWARP + copies - 1) / copies : 1;
+    a.flush_every = (1u << 31) / (32u * RI * TILE * 2u * sharers);
+    if (a.flush_every < 1u) a.flush_every = 1u;
+  }
+  const size_t smem = 2 * 3 * TILE * sizeof(float) + 2 * (size_t)QS * TPB * 4 +
+                      (size_t)copies * per_copy;
   CUDA_TRY(cudaFuncSetAttribute(pair_tile_kernel<BOXKIND>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));

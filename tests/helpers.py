@@ -45,5 +45,6 @@ def reference_rdf(count, volume, n_frames, nA, nB, edges, exclusion_block=None):
         N -= xA * xB * (nA / xA)
     vol = np.power(edges[1:], 3) - np.power(edges[:-1], 3)
     vol *= 4 / 3.0 * np.pi
-    density = N / (volume / n_frames)
-    return count / (density * vol * n_frames)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        density = np.float64(N) / (np.float64(volume) / n_frames)
+        return count / (density * vol * n_frames)
