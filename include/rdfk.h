@@ -118,6 +118,11 @@ int rdfk_rdf_sites(const float *xyz, int F, int natoms, const int *idxA,
 int rdfk_rdf_stats(const void *workspace, unsigned long long *out_host,
                    void *stream);
 
+/* number of CUDA kernels this library has launched since it was loaded
+ * (all streams, all devices); bench.py reports the difference over its timed
+ * region as `gpu_launches`.                                                   */
+unsigned long long rdfk_launch_count(void);
+
 /* FP32 roofline denominator: runs a dependent-chain-free FFMA kernel on every
  * SM and returns the achieved TFLOP/s (2 flop per FFMA lane).  Synchronises. */
 int rdfk_measure_fp32_peak(double *tflops_host, void *stream);

@@ -45,6 +45,8 @@ def _declare(L):
     L.rdfk_rdf_stats.restype = c_int
     L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
                                  c_void_p]
+    L.rdfk_launch_count.restype = ctypes.c_ulonglong
+    L.rdfk_launch_count.argtypes = []
     L.rdfk_measure_fp32_peak.restype = c_int
     L.rdfk_measure_fp32_peak.argtypes = [ctypes.POINTER(c_double), c_void_p]
 
@@ -52,7 +54,7 @@ def _declare(L):
 #: every symbol include/rdfk.h declares
 EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
-           "rdfk_rdf_stats", "rdfk_measure_fp32_peak")
+           "rdfk_rdf_stats", "rdfk_launch_count", "rdfk_measure_fp32_peak")
 
 
 def lib():
@@ -121,6 +123,10 @@ def rdf_stats(workspace, stream):
                                ctypes.c_void_p(int(stream))))
     return {"slow_pairs": int(out[0]), "all_slow_frames": int(out[1]),
             "tile_items": int(out[2]), "tile_pairs": int(out[3])}
+
+
+def launch_count():
+    return int(lib().rdfk_launch_count())
 
 
 def measure_fp32_peak(stream=0):

@@ -44,6 +44,10 @@
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
+// number of kernels this library has launched (bench.py's gpu_launches)
+static unsigned long long g_launches = 0;
+#define COUNT_LAUNCH(n) __atomic_fetch_add(&g_launches, (unsigned long long)(n), __ATOMIC_RELAXED)
+
 static int set_err(int code, const char *fmt, const char *a = "",
                    const char *b = "") {
   snprintf(g_err, sizeof(g_err), fmt, a, b);
@@ -1026,6 +1030,7 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   float *g2 = reinterpret_cast<float *>(ws + L.g2);
 
   init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(header, extents, F);
+  COUNT_LAUNCH(same_group ? 3 : 4);  // init + stage(s) + tables
   stage_kernel<BOXKIND><<<dim3(L.np1 / 256, F), 256, 0, st>>>(
       xyz, natoms, idx1, n1, L.np1, box, g1, extents);
   if (!same_group)
@@ -1073,8 +1078,10 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   if (occ < 1) return set_err(RDFK_ECUDA, "pair_tile_kernel does not fit%s%s");
   long long grid = (long long)sms * occ;
   if (grid > total) grid = total;
-  if (grid > 0)
+  if (grid > 0) {
     pair_tile_kernel<BOXKIND><<<(int)grid, TPB, smem, st>>>(a);
+    COUNT_LAUNCH(1);
+  }
 
   if (excl_a > 0 && excl_b > 0) {
     const size_t sm = (size_t)hp.nbins * sizeof(unsigned int);
@@ -1084,6 +1091,7 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
                                     (int)sm));
     excl_kernel<BOXKIND><<<dim3((n1 + 255) / 256, F), 256, sm, st>>>(
         g1, g2, L.np1, L.np2, n1, n2, excl_a, excl_b, fparams, hp, hist);
+    COUNT_LAUNCH(1);
   }
   CUDA_TRY(cudaGetLastError());
   return RDFK_OK;
@@ -1180,8 +1188,13 @@ extern "C" int rdfk_rdf_sites(const float *xyz, int F, int natoms,
           xyz, natoms, idxA, idxB, offA, offB, cell_off, n_sites, total_cells,
           box, hp, count);
   }
+  COUNT_LAUNCH(1);
   CUDA_TRY(cudaGetLastError());
   return RDFK_OK;
+}
+
+extern "C" unsigned long long rdfk_launch_count(void) {
+  return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
 }
 
 extern "C" int rdfk_rdf_stats(const void *workspace,
