@@ -11,19 +11,29 @@
 // Kernel plan (one rdfk_rdf_hist call == one block of F frames):
 //   init_ws_kernel    reset work counter / stats / extents
 //   stage_kernel      gather AtomGroup indices, AoS xyz -> SoA x|y|z per frame,
-//                     NaN-pad to the tile size, triclinic wrap, per-frame extents
-//   tables_kernel     per-frame fp32 decision tables: for every bin k the
-//                     interval [lo_k, hi_k) of *fp32 squared distance* for which
-//                     the fp64 reference provably lands in bin k
-//   pair_tile_kernel  persistent CTAs pull (frame, i-tile, j-tile) work items
-//                     from an atomic counter; the j-tile is staged into shared
-//                     memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier,
-//                     double buffered); each thread keeps RI i-atoms in
-//                     registers; fp32 minimum image, no sqrt unless the pair is
-//                     inside the cut-off; pairs that fall outside every
-//                     [lo_k, hi_k) are re-evaluated in fp64 with the reference's
-//                     exact operation order; counts go to warp-private shared
-//                     histograms, merged per CTA, then 64-bit global atomics
+//                     NaN-pad, triclinic wrap, per-frame extents
+//   tables_kernel     per-frame parameters and fp32 decision tables: for every
+//                     bin k the interval [lo_k, hi_k) of *fp32 squared
+//                     distance* for which the fp64 reference provably lands in
+//                     bin k; pruning slack, cell grid, shift validity
+//   key/scan/scatter  counting sort of every frame's atoms along a Hilbert
+//                     curve over a 2^b cubed cell grid (sorted SoA copy)
+//   bbox_kernel       bounding boxes of every 8-atom j-group and every
+//                     128-atom i-cluster of the sorted order
+//   pair_prune_kernel persistent warps pull (frame, i-cluster) work items from
+//                     an atomic counter; each lane keeps RI i-atoms in
+//                     registers; 32 j-group boxes are tested per ballot against
+//                     the cluster box (exact lower bound on the minimum-image
+//                     distance, so nothing in range is ever skipped); surviving
+//                     groups are staged into shared memory with cp.async
+//                     (double buffered) and evaluated on the FP32 pipe: one
+//                     lattice shift per (cluster, group) where provably valid
+//                     (6 instructions per pair), per-pair minimum image
+//                     otherwise; no sqrt unless the pair is inside the cut-off;
+//                     pairs that fall outside every [lo_k, hi_k) are
+//                     re-evaluated in fp64 with the reference's exact operation
+//                     order; counts go to warp-private shared histograms,
+//                     merged per CTA, then 64-bit global atomics
 //   excl_kernel       subtracts the exclusion_block pairs (exact, tiny)
 //   sites_kernel      InterRDF_s: one thread per (frame, site cell), fp64 only
 //
@@ -35,6 +45,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "rdfk.h"
@@ -67,9 +78,12 @@ static int set_err(int code, const char *fmt, const char *a = "",
 // ---------------------------------------------------------------------------
 constexpr int TPB = 256;         // threads per CTA (8 warps)
 constexpr int NWARP = TPB / 32;
-constexpr int RI = 4;            // i-atoms held in registers per thread
-constexpr int TILE = TPB * RI;   // atoms per i-tile == atoms per j-tile
-constexpr int HIST_SMEM_BUDGET = 96 * 1024;  // bytes for warp-private copies
+constexpr int RI = 4;            // i-atoms held in registers per lane
+constexpr int CI = 32 * RI;      // atoms per i-cluster (one warp work item)
+constexpr int GJ = 8;            // atoms per j-group (pruning granule)
+constexpr int GPC = CI / GJ;     // j-groups per cluster
+constexpr int TILE = CI;         // padding granule of the staged arrays
+constexpr int HIST_SMEM_BUDGET = 32 * 1024;  // bytes for warp-private copies
 constexpr float MAGIC = 12582912.0f;         // 1.5 * 2^23: rint via add/sub
 constexpr double EPS32 = 5.9604644775390625e-8;  // 2^-24
 
@@ -85,6 +99,17 @@ struct FrameParams {
   float inv_dr;   // nbins / (r1 - r0)
   float koff;     // -r0 * inv_dr
   int all_slow;   // fast path not provably safe for this frame
+  // sorting / pruning.  "prune space" u: ortho and no-box = Cartesian offset
+  // from `org`, wrapped into [0, L) on periodic axes; triclinic = fractional
+  // coordinates of the wrapped atom.
+  float org[3];     // origin of prune space (per-frame minimum coordinate)
+  float per[3];     // period in prune space (+inf: axis not periodic)
+  float gscale[3];  // u * gscale in [0, 1): position inside the cell grid
+  float wk[3];      // prune-space gap -> distance lower bound
+  float rprune;     // group pair skipped iff bound > rprune
+  float rshift;     // margin for the one-shift-per-group fast path
+  int shift_ok;     // frame allows the shifted variant
+  int prune_ok;     // 0: boxes are infinite (nothing is skipped)
 };
 
 struct HistParams {
@@ -100,9 +125,17 @@ struct WsHeader {
 };
 
 struct WsLayout {
-  size_t header, extents, fparams, tables, g1, g2, total;
-  int np1, np2;
+  size_t header, extents, fparams, tables, g1, g2, s1, s2, gbb1, gbb2, cbb1,
+      cbb2, keys, lrank, cells, total;
+  int np1, np2, bits1, bits2;
 };
+
+// cells per axis = 2^bits: about two atoms per cell
+static inline int grid_bits(int n) {
+  int bits = 1;
+  while (bits < 7 && (1ll << (3 * (bits + 1))) <= (long long)n) ++bits;
+  return bits;
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -124,6 +157,33 @@ static WsLayout ws_layout(int F, int n1, int n2, int nbins, int same_group) {
   w.g2 = same_group ? w.g1 : off;
   if (!same_group)
     off = align_up(off + sizeof(float) * 3 * (size_t)w.np2 * (size_t)F, 256);
+  // sorted copies, group / cluster boxes
+  w.s1 = off;
+  off = align_up(off + sizeof(float) * 3 * (size_t)w.np1 * (size_t)F, 256);
+  w.s2 = same_group ? w.s1 : off;
+  if (!same_group)
+    off = align_up(off + sizeof(float) * 3 * (size_t)w.np2 * (size_t)F, 256);
+  w.gbb1 = off;
+  off = align_up(off + sizeof(float) * 6 * (size_t)(w.np1 / GJ) * (size_t)F, 256);
+  w.gbb2 = same_group ? w.gbb1 : off;
+  if (!same_group)
+    off = align_up(off + sizeof(float) * 6 * (size_t)(w.np2 / GJ) * (size_t)F, 256);
+  w.cbb1 = off;
+  off = align_up(off + sizeof(float) * 6 * (size_t)(w.np1 / CI) * (size_t)F, 256);
+  w.cbb2 = same_group ? w.cbb1 : off;
+  if (!same_group)
+    off = align_up(off + sizeof(float) * 6 * (size_t)(w.np2 / CI) * (size_t)F, 256);
+  // counting-sort scratch, shared by the two groups (used one after the other)
+  const int npmax = w.np1 > w.np2 ? w.np1 : w.np2;
+  w.bits1 = grid_bits(n1);
+  w.bits2 = same_group ? w.bits1 : grid_bits(n2);
+  const int bmax = w.bits1 > w.bits2 ? w.bits1 : w.bits2;
+  w.keys = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)npmax * (size_t)F, 256);
+  w.lrank = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)npmax * (size_t)F, 256);
+  w.cells = off;
+  off = align_up(off + sizeof(uint32_t) * ((size_t)1 << (3 * bmax)) * (size_t)F, 256);
   w.total = off;
   return w;
 }
@@ -142,50 +202,6 @@ __device__ __forceinline__ float ordered_to_float(int i) {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(count)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src,
-                                         uint32_t bytes, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0u;
-}
-// The wait loop is written in C++ (not as branches inside the asm) so that the
-// compiler sees the divergence and re-converges the warp afterwards: with the
-// loop hidden in inline PTX, lanes leaving try_wait at different times stayed
-// split for the whole tile and every instruction issued twice (ncu: 16.8
-// active threads per instruction, profiles/r1_notes.md).
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-  __syncwarp();
-}
-
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -413,6 +429,7 @@ __global__ __launch_bounds__(256) void stage_kernel(
 // Band derivation: DESIGN.md section 3.
 __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
                               const int *__restrict__ extents, HistParams hp,
+                              int debug_flags,
                               FrameParams *__restrict__ fparams,
                               float2 *__restrict__ tables) {
   const int f = blockIdx.x;
@@ -421,20 +438,35 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
   FrameParams *fp = fparams + f;
   if (threadIdx.x == 0) {
     const int *e = extents + f * 6;
-    double X[3];
-    bool slow = false;
+    double X[3], A[3], lo3[3];
+    bool slow = false, finite = true;
     for (int k = 0; k < 3; ++k) {
       const double lo = ordered_to_float(e[k]), hi = ordered_to_float(e[3 + k]);
       X[k] = (hi >= lo) ? (hi - lo) * (1.0 + 1e-6) : 0.0;
+      A[k] = (hi >= lo) ? fmax(fabs(lo), fabs(hi)) : 0.0;
+      lo3[k] = (hi >= lo) ? lo : 0.0;
       if (!(X[k] < 1e30)) slow = true;
+      if (!(X[k] < 1e15) || !(A[k] < 1e15)) finite = false;
     }
     double dk[3] = {0.0, 0.0, 0.0};
     const float *b = box + (size_t)f * 9;
     for (int k = 0; k < 3; ++k) {
       fp->L[k] = fp->inv[k] = fp->fl[k] = fp->finv[k] = 0.f;
       fp->tinv[k] = 0.f;
+      fp->org[k] = (float)lo3[k];
+      fp->per[k] = INFINITY;
+      fp->wk[k] = 1.f;
+      // no box / non-periodic axis: the grid spans the extents
+      fp->gscale[k] = (float)(1.0 / (X[k] * (1.0 + 1e-6) + 1e-30));
+      if (!(fp->gscale[k] < 1e30f)) fp->gscale[k] = 0.f;
     }
     for (int k = 0; k < 9; ++k) fp->tri[k] = 0.f;
+    const double rmax = hp.r1;
+    // slack of the pruning bound: fp32 evaluation of the prune-space
+    // coordinates and boxes, and the reference's own rounding (all ~1e-7
+    // relative to the coordinate scale; 1e-5 leaves two orders of margin)
+    double scale = 0.0;
+    bool shift_ok = (boxkind == RDFK_BOX_ORTHO);
     if (boxkind == RDFK_BOX_ORTHO) {
       for (int k = 0; k < 3; ++k) {
         const float L = b[k];
@@ -443,17 +475,27 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
         if (L > FLT_EPSILON) {
           fp->fl[k] = L;
           fp->finv[k] = fp->inv[k];
-          dk[k] = EPS32 * (X[k] + 0.5 * (double)L) * 1.01;
+          fp->per[k] = L;
+          fp->gscale[k] = (float)(1.0 / (double)L);
           if (!(X[k] * (double)fp->inv[k] < 2097152.0)) slow = true;
+          scale = fmax(scale, A[k] + X[k] + (double)L);
+          // shifted variant: every atom must be its own wrapped image
+          // (same fp32 expression as prune_coords; monotonic in x)
+          const float hi = ordered_to_float(e[3 + k]);
+          const float t = __fmul_rn(__fsub_rn(hi, fp->org[k]), fp->finv[k]);
+          if (!(X[k] > 0.0 ? t < 1.0f : true)) shift_ok = false;
+          if (!(rmax * 1.01 < 0.5 * (double)L)) shift_ok = false;
         } else if (!(L <= FLT_EPSILON)) {
           slow = true;  // NaN box length
+          finite = false;
+        } else {
+          scale = fmax(scale, A[k] + X[k]);
         }
       }
     } else if (boxkind == RDFK_BOX_TRI) {
       for (int k = 0; k < 9; ++k) fp->tri[k] = b[k];
       const double ax = b[0], bx = b[3], by = b[4], cx = b[6], cy = b[7],
                    cz = b[8];
-      const double rmax = hp.r1;
       // fast path validity: the in-range image must be unique, inside the
       // brick, and among the reference's 27 images
       bool ok = ax > 0 && by > 0 && cz > 0 && b[1] == 0.f && b[2] == 0.f &&
@@ -479,14 +521,61 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
             !((X[0] + (fabs(cx) + fabs(bx)) * 1e3 + ax) / ax < 2097152.0))
           slow = true;
       }
+      // prune space = fractional coordinates; a fractional gap g along lattice
+      // direction k is at least g * (distance between the faces k) apart
+      const bool cell_ok = ax > 0 && by > 0 && cz > 0 && b[1] == 0.f &&
+                           b[2] == 0.f && b[5] == 0.f;
+      if (cell_ok) {
+        const double n_a = sqrt(by * cz * by * cz + bx * cz * bx * cz +
+                                (bx * cy - by * cx) * (bx * cy - by * cx));
+        const double w_a = ax * by * cz / n_a;
+        const double w_b = by * cz / sqrt(cz * cz + cy * cy);
+        const double w_c = cz;
+        fp->wk[0] = (float)(w_a * (1.0 - 1e-6));
+        fp->wk[1] = (float)(w_b * (1.0 - 1e-6));
+        fp->wk[2] = (float)(w_c * (1.0 - 1e-6));
+        for (int k = 0; k < 3; ++k) {
+          fp->org[k] = 0.f;
+          fp->per[k] = 1.f;
+          fp->gscale[k] = 1.f;
+        }
+        scale = A[0] + A[1] + A[2] + fabs(ax) + fabs(bx) + fabs(by) +
+                fabs(cx) + fabs(cy) + fabs(cz);
+        // fractional coordinates lose accuracy in very flat cells
+        if (!(fmin(w_a, fmin(w_b, w_c)) > 1e-3 * scale)) finite = false;
+      } else {
+        finite = false;
+      }
+    } else {
+      for (int k = 0; k < 3; ++k) scale = fmax(scale, A[k] + X[k]);
+    }
+    const double slack = 2e-5 * scale;
+    const double R = rmax * 1.001 + slack;
+    if (boxkind == RDFK_BOX_ORTHO) {
+      for (int k = 0; k < 3; ++k) {
+        if (!(fp->fl[k] > 0.f)) continue;
+        // generic variant: eps (X + L/2); shifted variant: eps (A + 2R + 2X)
+        dk[k] = EPS32 * (X[k] + 0.5 * (double)fp->fl[k]) * 1.01;
+        if (shift_ok) dk[k] = EPS32 * (A[k] + 2.0 * R + 2.0 * X[k] +
+                                       0.5 * (double)fp->fl[k]) * 1.01;
+      }
     }
     const double delta = sqrt(dk[0] * dk[0] + dk[1] * dk[1] + dk[2] * dk[2]);
     if (!(delta < 1e30)) slow = true;
+    if (slow) shift_ok = false;
     s_delta = delta;
     s_slow = slow ? 1 : 0;
     fp->all_slow = slow ? 1 : 0;
     fp->inv_dr = (float)((double)hp.nbins / (hp.r1 - hp.r0));
     fp->koff = (float)(-hp.r0 * ((double)hp.nbins / (hp.r1 - hp.r0)));
+    fp->rprune = (float)((rmax + slack) * (1.0 + 1e-6));
+    fp->rshift = (float)((R + 8.0 * delta) * (1.0 + 1e-6));
+    if (shift_ok)
+      for (int k = 0; k < 3; ++k)
+        if (fp->fl[k] > 0.f && !((double)fp->rshift < 0.4999 * (double)fp->fl[k]))
+          shift_ok = false;
+    fp->shift_ok = (shift_ok && !(debug_flags & 2)) ? 1 : 0;
+    fp->prune_ok = (finite && slack < 1e15 && !(debug_flags & 1)) ? 1 : 0;
   }
   __syncthreads();
   const double delta = s_delta;
@@ -521,79 +610,349 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
 }
 
 // ---------------------------------------------------------------------------
-// the tile kernel
+// the sort + prune + pair kernels
 // ---------------------------------------------------------------------------
+
+// prune-space coordinates of one (staged) atom; see FrameParams
+template <int BOXKIND>
+__device__ __forceinline__ void prune_coords(float x, float y, float z,
+                                             const FrameParams &p, float &u0,
+                                             float &u1, float &u2) {
+  if (BOXKIND == RDFK_BOX_TRI) {
+    const float sc = __fmul_rn(z, p.tinv[2]);
+    const float sb = __fmul_rn(__fmaf_rn(-sc, p.tri[7], y), p.tinv[1]);
+    const float sa = __fmul_rn(
+        __fmaf_rn(-sc, p.tri[6], __fmaf_rn(-sb, p.tri[3], x)), p.tinv[0]);
+    u0 = sa; u1 = sb; u2 = sc;
+  } else {
+    float c[3] = {__fsub_rn(x, p.org[0]), __fsub_rn(y, p.org[1]),
+                  __fsub_rn(z, p.org[2])};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (p.fl[k] > 0.f)
+        c[k] = __fmaf_rn(-p.fl[k], floorf(__fmul_rn(c[k], p.finv[k])), c[k]);
+    u0 = c[0]; u1 = c[1]; u2 = c[2];
+  }
+}
+
+// Hilbert index of cell (x, y, z) on a 2^bits cubed grid (Skilling's
+// transpose algorithm).  Only locality depends on it, never correctness.
+__device__ __forceinline__ uint32_t hilbert3(uint32_t x, uint32_t y, uint32_t z,
+                                             int bits) {
+  uint32_t X[3] = {x, y, z};
+  const uint32_t M = 1u << (bits - 1);
+  for (uint32_t Q = M; Q > 1; Q >>= 1) {
+    const uint32_t P = Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q) {
+        X[0] ^= P;
+      } else {
+        const uint32_t t = (X[0] ^ X[i]) & P;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];
+  X[2] ^= X[1];
+  uint32_t t = 0;
+  for (uint32_t Q = M; Q > 1; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  uint32_t key = 0;
+  for (int b = bits - 1; b >= 0; --b)
+    key = (key << 3) | (((X[0] >> b) & 1u) << 2) | (((X[1] >> b) & 1u) << 1) |
+          ((X[2] >> b) & 1u);
+  return key;
+}
+
+// counting sort, pass 1: cell key of every atom + its arrival rank in the cell
+template <int BOXKIND>
+__global__ __launch_bounds__(256) void key_kernel(
+    const float *__restrict__ staged, int n, int np,
+    const FrameParams *__restrict__ fparams, int bits,
+    uint32_t *__restrict__ keys, uint32_t *__restrict__ lrank,
+    uint32_t *__restrict__ cells) {
+  const int f = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const FrameParams &p = fparams[f];
+  const float *g = staged + (size_t)f * 3 * np;
+  float u0, u1, u2;
+  prune_coords<BOXKIND>(g[a], g[(size_t)np + a], g[2 * (size_t)np + a], p, u0,
+                        u1, u2);
+  const int m = 1 << bits;
+  const float fm = (float)m;
+  // NaN -> 0, out-of-grid -> clamped (pruning uses the real boxes anyway)
+  int c0 = __float2int_rd(__fmul_rn(__fmul_rn(u0, p.gscale[0]), fm));
+  int c1 = __float2int_rd(__fmul_rn(__fmul_rn(u1, p.gscale[1]), fm));
+  int c2 = __float2int_rd(__fmul_rn(__fmul_rn(u2, p.gscale[2]), fm));
+  c0 = max(0, min(m - 1, c0));
+  c1 = max(0, min(m - 1, c1));
+  c2 = max(0, min(m - 1, c2));
+  const uint32_t key = hilbert3((uint32_t)c0, (uint32_t)c1, (uint32_t)c2, bits);
+  const size_t ncell = (size_t)1 << (3 * bits);
+  keys[(size_t)f * np + a] = key;
+  lrank[(size_t)f * np + a] = atomicAdd(cells + (size_t)f * ncell + key, 1u);
+}
+
+// pass 2: exclusive prefix sum of the cell counts, one CTA per frame
+__global__ __launch_bounds__(1024) void scan_kernel(uint32_t *__restrict__ cells,
+                                                    int ncell) {
+  uint32_t *c = cells + (size_t)blockIdx.x * ncell;
+  const int tid = threadIdx.x;
+  const int strip = (ncell + 1023) / 1024;
+  const int lo = min(ncell, tid * strip), hi = min(ncell, lo + strip);
+  uint32_t s = 0;
+  for (int i = lo; i < hi; ++i) s += c[i];
+  __shared__ uint32_t wsum[32];
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = wsum[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+      if (tid >= o) w += v;
+    }
+    wsum[tid] = w;
+  }
+  __syncthreads();
+  uint32_t run = incl - s + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0u);
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t v = c[i];
+    c[i] = run;
+    run += v;
+  }
+}
+
+// pass 3: scatter into Hilbert order (SoA), NaN in the padded tail
+__global__ __launch_bounds__(256) void scatter_kernel(
+    const float *__restrict__ staged, int n, int np, int bits,
+    const uint32_t *__restrict__ keys, const uint32_t *__restrict__ lrank,
+    const uint32_t *__restrict__ cells, float *__restrict__ sorted) {
+  const int f = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= np) return;
+  const float *g = staged + (size_t)f * 3 * np;
+  float *o = sorted + (size_t)f * 3 * np;
+  if (a < n) {
+    const size_t ncell = (size_t)1 << (3 * bits);
+    const uint32_t pos = cells[(size_t)f * ncell + keys[(size_t)f * np + a]] +
+                         lrank[(size_t)f * np + a];
+    o[pos] = g[a];
+    o[(size_t)np + pos] = g[(size_t)np + a];
+    o[2 * (size_t)np + pos] = g[2 * (size_t)np + a];
+  } else {
+    const float nan = __int_as_float(0x7fc00000);
+    o[a] = nan;
+    o[(size_t)np + a] = nan;
+    o[2 * (size_t)np + a] = nan;
+  }
+}
+
+// Boxes in prune space: one thread per 8-atom group; 16 neighbouring threads
+// combine into the 128-atom cluster box.  Layout [F][6][count]:
+// centre x|y|z, half-width x|y|z.  Empty box: half-width -inf (never
+// reached); frame without pruning: half-width +inf (always reached).
+template <int BOXKIND>
+__global__ __launch_bounds__(256) void bbox_kernel(
+    const float *__restrict__ sorted, int np,
+    const FrameParams *__restrict__ fparams, float *__restrict__ gbb,
+    float *__restrict__ cbb) {
+  const int f = blockIdx.y;
+  const int ngrp = np / GJ, ncl = np / CI;   // ngrp is a multiple of GPC
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = gt < ngrp;
+  const int g = live ? gt : ngrp - 1;
+  const FrameParams &p = fparams[f];
+  const float *s = sorted + (size_t)f * 3 * np + (size_t)g * GJ;
+  float lo[3] = {INFINITY, INFINITY, INFINITY};
+  float hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int u = 0; u < GJ; ++u) {
+    const float x = s[u], y = s[(size_t)np + u], z = s[2 * (size_t)np + u];
+    float c[3];
+    prune_coords<BOXKIND>(x, y, z, p, c[0], c[1], c[2]);
+    // atoms with a non-finite coordinate never produce a finite distance
+    if (isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2])) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = fminf(lo[k], c[k]);
+        hi[k] = fmaxf(hi[k], c[k]);
+      }
+    }
+  }
+  const bool noprune = !p.prune_ok;
+  auto emit = [&](float *dst, int count, int at, const float *l, const float *h) {
+    float *d = dst + (size_t)f * 6 * count;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float c, w;
+      if (noprune) { c = 0.f; w = INFINITY; }
+      else if (!(h[k] >= l[k])) { c = 0.f; w = -INFINITY; }
+      else {
+        c = __fmul_rn(0.5f, __fadd_rn(l[k], h[k]));
+        // half-width rounded up so that [c - w, c + w] covers [l, h]
+        w = fmaxf(__fsub_rn(h[k], c), __fsub_rn(c, l[k]));
+        w = __fmaf_rn(w, 1.0f + 1e-6f, 1e-30f);
+      }
+      d[(size_t)k * count + at] = c;
+      d[(size_t)(3 + k) * count + at] = w;
+    }
+  };
+  if (live) emit(gbb, ngrp, g, lo, hi);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+  }
+  if (live && (g & (GPC - 1)) == 0) emit(cbb, ncl, g / GPC, lo, hi);
+}
+
 struct PairArgs {
-  const float *g1;  // staged [F][3][np1]
-  const float *g2;  // staged [F][3][np2]
-  int np1, np2, n1, n2, F;
-  int nt1, nt2;          // tiles per group
-  int symmetric;         // circulant half-matrix schedule over nt1 == nt2
-  int items_per_frame;
-  int total_items;
+  const float *gi;   // sorted [F][3][np_i]: the side whose clusters are work items
+  const float *gj;   // sorted [F][3][np_j]
+  const float *cbb;  // cluster boxes of the i side [F][6][ncl_i]
+  const float *gbb;  // group boxes of the j side   [F][6][ngrp_j]
+  int np_i, np_j, F;
+  int n_i, n_j;      // real atoms (the sorted arrays hold them first)
+  int ncl_i, ngrp_j;
+  int symmetric;     // gi == gj: circulant half of the cluster matrix
+  int swapped;       // i side is the reference's g2 (`conf`), j side its g1
+  int total_items;   // F * ncl_i
   const FrameParams *fparams;
   const float2 *tables;
   HistParams hp;
-  int hist_copies;       // warp-private shared copies (0 = global atomics)
-  unsigned int flush_every;  // items between 32-bit shared-counter flushes
+  int hist_copies;   // warp-private shared copies (0 = global atomics)
   unsigned long long *hist;
   WsHeader *header;
 };
 
 // ---------------------------------------------------------------------------
-// In-range pairs are a minority (0.1-16 % of evaluated pairs) scattered over
-// the lanes of a warp, so binning them where they are found wastes the warp on
-// divergence (measured: 2.8x slower, tools/ubench2.cu).  Instead every thread
-// appends its hits to a private queue in shared memory with three predicated
-// instructions (no branch), and the warp drains all queues at warp-uniform
-// points.  A queue entry is (fp32 r2, j-step); the i-atom is implied by the
-// owning thread.  The rare band failure recovers the exact (u, r) pair by
-// re-evaluating the 4*RI candidates of that j-step (resolve_band).
+// In-range pairs are a minority scattered over the lanes of a warp, so binning
+// them where they are found wastes the warp on divergence (measured 2.8x
+// slower, tools/ubench2.cu).  Instead every lane appends the fp32 r2 of its
+// hits to a private queue in shared memory with three predicated instructions
+// (no branch), and the warp drains all queues at warp-uniform points.  The
+// pair behind an entry is implied: the warp logs the j-groups it evaluated
+// since the last drain and every lane marks its queue length at each group
+// start, so the rare band failure re-scans one group (resolve_entry).
 // ---------------------------------------------------------------------------
-constexpr int QS = 16;                 // queue slots per thread
-constexpr int Q_STRIDE = TPB * 4;      // bytes between slots of one thread
-constexpr int Q_JOFF = QS * TPB * 4;   // byte offset of the j-step array
-constexpr int Q_CHECK = 2;             // drain check every Q_CHECK u-steps
-static_assert(QS >= 2 * Q_CHECK * RI, "queue must absorb one check interval");
+constexpr int QS = 64;        // queue slots per lane
+constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
+constexpr int NST = 2;        // cp.async staging slots per warp
+constexpr int PAIRS_PER_GROUP = GJ * RI;   // per lane
+static_assert(QS >= 2 * PAIRS_PER_GROUP, "queue must absorb one group");
+static_assert(QS < 256, "marks are bytes");
 
-__device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut,
-                                       uint32_t jb) {
+constexpr int SM_Q = QS * 32 * 4;              // bytes per warp: queue
+constexpr int SM_ST = NST * 3 * GJ * 4;        // staging ring
+constexpr int SM_LOG = LOGMAX * 4;             // group log
+constexpr int SM_MARK = LOGMAX * 32;           // queue marks (bytes)
+constexpr int SM_WARP = SM_Q + SM_ST + SM_LOG + SM_MARK;
+
+__device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.lt.f32 p, %1, %2;\n"
       "@p st.shared.f32 [%0], %1;\n"
-      "@p st.shared.u32 [%0+%4], %3;\n"
-      "@p add.u32 %0, %0, %5;\n"
+      "@p add.u32 %0, %0, 128;\n"
       "}\n"
       : "+r"(qaddr)
-      : "f"(r2), "f"(cut), "r"(jb), "n"(Q_JOFF), "n"(Q_STRIDE)
+      : "f"(r2), "f"(cut)
       : "memory");
 }
 
-// Rare path: the `rank`-th (0-based, in (u, r) scan order) pair of j-step `jb`
-// whose fp32 r2 equals `r2` bit for bit; returns its exact bin (or -1).
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// group code: bits 0-1 nx+1, 2-3 ny+1, 4-5 nz+1, bit 6 = one shift is valid
+__device__ __forceinline__ void decode_shift(int code, const FastBox &fb,
+                                             float &sx, float &sy, float &sz) {
+  sx = __fmul_rn((float)((code & 3) - 1), fb.l0);
+  sy = __fmul_rn((float)(((code >> 2) & 3) - 1), fb.l1);
+  sz = __fmul_rn((float)(((code >> 4) & 3) - 1), fb.l2);
+}
+constexpr int CODE_PLAIN = 64;
+constexpr int CODE_ZERO = 1 | (1 << 2) | (1 << 4);
+
+// r2 of one pair.  PLAIN: the i coordinates already carry the lattice shift.
+template <int BOXKIND, bool PLAIN>
+__device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float xi,
+                                         float yi, float zi, const FastBox &fb) {
+  const float dx = __fsub_rn(xj, xi), dy = __fsub_rn(yj, yi),
+              dz = __fsub_rn(zj, zi);
+  if (PLAIN || BOXKIND == RDFK_BOX_NONE)
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return r2_fast<BOXKIND>(dx, dy, dz, fb);
+}
+
+// Rare path: entry `s` of this lane's queue failed the band test.  Find the
+// group it came from (marks), re-scan that group in the hot loop's order with
+// the hot loop's arithmetic, and bin the pair with the reference arithmetic.
 template <int BOXKIND>
-__device__ __noinline__ int resolve_band(
-    float r2, uint32_t jb, int rank, const float *xs, float x0, float x1,
-    float x2, float x3, float y0, float y1, float y2, float y3, float z0,
-    float z1, float z2, float z3, const FrameParams *__restrict__ fp,
+__device__ __noinline__ int resolve_entry(
+    int s, int lane, const unsigned char *mark, const int *glog, int nlog,
+    const float *gi_cl, size_t np_i, const float *gj_f, size_t np_j,
+    float r2_cut, int swapped, const FrameParams *__restrict__ fp,
     const HistParams *__restrict__ hp) {
+  int e = 0;
+  for (int t = 1; t < nlog; ++t)
+    if ((int)mark[t * 32 + lane] <= s) e = t;
+  int rank = s - (int)mark[e * 32 + lane];
+  const int packed = glog[e];
+  const int g = packed & 0xffffff, code = (packed >> 24) & 0x7f;
   const FastBox fb = load_fastbox(fp);
-  const float xi[4] = {x0, x1, x2, x3}, yi[4] = {y0, y1, y2, y3},
-              zi[4] = {z0, z1, z2, z3};
-  const float *ys = xs + TILE, *zs = xs + 2 * TILE;
-  int seen = 0;
-  for (int u = 0; u < 4; ++u) {
-    const float xj = xs[jb + u], yj = ys[jb + u], zj = zs[jb + u];
+  const bool plain = (BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN);
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (BOXKIND == RDFK_BOX_ORTHO && plain) decode_shift(code, fb, sx, sy, sz);
+  float xr[RI], yr[RI], zr[RI];
+#pragma unroll
+  for (int r = 0; r < RI; ++r) {
+    xr[r] = gi_cl[r * 32 + lane];
+    yr[r] = gi_cl[np_i + r * 32 + lane];
+    zr[r] = gi_cl[2 * np_i + r * 32 + lane];
+  }
+  const float *js = gj_f + (size_t)g * GJ;
+  for (int u = 0; u < GJ; ++u) {
+    const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
-      const float v = r2_fast<BOXKIND>(__fsub_rn(xj, xi[r]), __fsub_rn(yj, yi[r]),
-                                       __fsub_rn(zj, zi[r]), fb);
-      if (__float_as_uint(v) == __float_as_uint(r2)) {
-        if (seen == rank)
-          return exact_bin<BOXKIND>(xi[r], yi[r], zi[r], xj, yj, zj, fp, hp);
-        ++seen;
+      float r2;
+      if (plain)
+        r2 = pair_r2<BOXKIND, true>(xj, yj, zj, __fadd_rn(xr[r], sx),
+                                    __fadd_rn(yr[r], sy), __fadd_rn(zr[r], sz),
+                                    fb);
+      else
+        r2 = pair_r2<BOXKIND, false>(xj, yj, zj, xr[r], yr[r], zr[r], fb);
+      if (r2 < r2_cut) {
+        if (rank == 0)
+          return swapped
+                     ? exact_bin<BOXKIND>(xj, yj, zj, xr[r], yr[r], zr[r], fp, hp)
+                     : exact_bin<BOXKIND>(xr[r], yr[r], zr[r], xj, yj, zj, fp, hp);
+        --rank;
       }
     }
   }
@@ -601,136 +960,111 @@ __device__ __noinline__ int resolve_band(
 }
 
 template <int BOXKIND>
-__global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
-  static_assert(RI == 4, "resolve_band takes four i-atoms");
+__global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
+  static_assert(RI == 4 && GJ == 8, "hot loop is written for 4 x 8");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float *jbuf = reinterpret_cast<float *>(smem_raw);            // [2][3][TILE]
-  float *q_r2 = jbuf + 2 * 3 * TILE;                            // [QS][TPB]
-  uint32_t *q_j = reinterpret_cast<uint32_t *>(q_r2 + QS * TPB);  // [QS][TPB]
-  unsigned int *hist_s = reinterpret_cast<unsigned int *>(q_j + QS * TPB);
-  __shared__ uint64_t bars[2];
-  __shared__ int s_next[2];
   __shared__ HistParams s_hp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char *wbase = smem_raw + (size_t)warp * SM_WARP;
+  float *q = reinterpret_cast<float *>(wbase);
+  float *jst = reinterpret_cast<float *>(wbase + SM_Q);
+  int *glog = reinterpret_cast<int *>(wbase + SM_Q + SM_ST);
+  unsigned char *mark = wbase + SM_Q + SM_ST + SM_LOG;
+  unsigned int *hist_s =
+      reinterpret_cast<unsigned int *>(smem_raw + (size_t)NWARP * SM_WARP);
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
   const int nbins = a.hp.nbins;
   const int copies = a.hist_copies;
   unsigned int *wh = copies ? hist_s + (size_t)(warp % copies) * nbins : nullptr;
-  const uint32_t qbase = smem_u32(q_r2 + tid);
+  const unsigned int sharers = copies ? (NWARP + copies - 1) / copies : 1;
+  const uint32_t qbase = smem_u32(q + lane);
   uint32_t qaddr = qbase;
 
   for (int b = tid; b < copies * nbins; b += TPB) hist_s[b] = 0u;
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    s_hp = a.hp;
-  }
+  if (tid == 0) s_hp = a.hp;
   __syncthreads();
 
-  auto decode = [&](int item, int &f, int &it, int &jt) {
-    f = item / a.items_per_frame;
-    const int w = item - f * a.items_per_frame;
-    if (a.symmetric) {
-      const int nt = a.nt1, B = (nt - 1) / 2 + 1;
-      if (w < nt * B) { it = w / B; jt = it + (w - it * B); }
-      else { it = w - nt * B; jt = it + nt / 2; }
-      if (jt >= nt) jt -= nt;
-    } else {
-      it = w / a.nt2; jt = w - it * a.nt2;
-    }
-  };
-  auto issue_load = [&](int item, int buf) {
-    // thread 0 only: j-tile of `item` -> jbuf[buf] by three 1-D TMA copies
-    int f, it, jt;
-    decode(item, f, it, jt);
-    const float *src = a.g2 + (size_t)f * 3 * a.np2 + (size_t)jt * TILE;
-    float *dst = jbuf + (size_t)buf * 3 * TILE;
-    mbar_expect_tx(&bars[buf], 3u * TILE * sizeof(float));
-    bulk_g2s(dst, src, TILE * sizeof(float), &bars[buf]);
-    bulk_g2s(dst + TILE, src + a.np2, TILE * sizeof(float), &bars[buf]);
-    bulk_g2s(dst + 2 * TILE, src + 2 * (size_t)a.np2, TILE * sizeof(float),
-             &bars[buf]);
-  };
+  unsigned int n_slow = 0, n_groups = 0, n_items = 0;
+  unsigned int added = 0;   // upper bound of what this warp put into one bin
 
-  // prologue: grab the first item and start its load
-  if (tid == 0) {
-    const int first = atomicAdd(&a.header->work_counter, 1);
-    s_next[0] = first;
-    if (first < a.total_items) issue_load(first, 0);
-  }
-  __syncthreads();
-
-  unsigned int n_slow = 0;
-  unsigned int n_items = 0;
-  uint32_t phase0 = 0u, phase1 = 0u;
-  int buf = 0;
-  int cur = s_next[0];
-
-  while (cur < a.total_items) {
-    // fetch the next item and prefetch its j-tile into the other buffer (all
-    // threads left that buffer at the __syncthreads closing the last round)
-    if (tid == 0) {
-      const int nxt = atomicAdd(&a.header->work_counter, 1);
-      s_next[buf ^ 1] = nxt;
-      if (nxt < a.total_items) issue_load(nxt, buf ^ 1);
-    }
-
-    int f, it, jt;
-    decode(cur, f, it, jt);
-    const unsigned int weight = (a.symmetric && it != jt) ? 2u : 1u;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&a.header->work_counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= a.total_items) break;
+    ++n_items;
+    const int f = item / a.ncl_i, ic = item - f * a.ncl_i;
     const FrameParams *fp = a.fparams + f;
     const float2 *tab = a.tables + (size_t)f * nbins;
     const FastBox fb = load_fastbox(fp);
     const float r2_cut = fp->r2_cut;
     const int all_slow = fp->all_slow;
+    const int shift_ok = fp->shift_ok;
+    const size_t np_i = (size_t)a.np_i, np_j = (size_t)a.np_j;
+    const float *gi_cl = a.gi + (size_t)f * 3 * np_i + (size_t)ic * CI;
+    const float *gj_f = a.gj + (size_t)f * 3 * np_j;
 
-    // my i-atoms (coalesced; NaN in the padded tail)
-    float xi[RI], yi[RI], zi[RI];
+    // cluster box (prune space)
+    float cc[3], ch[3];
     {
-      const float *g = a.g1 + (size_t)f * 3 * a.np1 + (size_t)it * TILE;
+      const float *cb = a.cbb + (size_t)f * 6 * a.ncl_i;
 #pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        xi[r] = g[r * TPB + tid];
-        yi[r] = g[(size_t)a.np1 + r * TPB + tid];
-        zi[r] = g[2 * (size_t)a.np1 + r * TPB + tid];
+      for (int k = 0; k < 3; ++k) {
+        cc[k] = cb[(size_t)k * a.ncl_i + ic];
+        ch[k] = cb[(size_t)(3 + k) * a.ncl_i + ic];
       }
     }
-    const int jcount = min(TILE, a.n2 - jt * TILE);
-    const float *xs = jbuf + (size_t)buf * 3 * TILE;
-    const float *ys = xs + TILE;
-    const float *zs = xs + 2 * TILE;
+    const float per[3] = {fp->per[0], fp->per[1], fp->per[2]};
+    const float wk[3] = {fp->wk[0], fp->wk[1], fp->wk[2]};
+    const float rprune = fp->rprune, rshift = fp->rshift;
 
-    if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
-    else { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
+    // i-atoms, shifted by the current group's lattice vector
+    int cur_code = -1;
+    float xs[RI], ys[RI], zs[RI];
+    auto set_shift = [&](int code) {
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      if (BOXKIND == RDFK_BOX_ORTHO && (code & CODE_PLAIN))
+        decode_shift(code, fb, sx, sy, sz);
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        xs[r] = __fadd_rn(gi_cl[r * 32 + lane], sx);
+        ys[r] = __fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
+        zs[r] = __fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
+      }
+      cur_code = code;
+    };
 
-    // bin everything queued so far (warp-uniform call sites only).  The loop
-    // bound is warp-uniform (REDUX max) and the per-lane work is a structured
-    // `if`: a per-lane trip count left the lanes split into sub-warps for the
-    // rest of the tile (BSYNC did not merge them; ncu showed 16.8 active
-    // threads per instruction in the hot loop).
+    int nlog = 0;
+    unsigned int weight = 1u;
+
+    // bin everything queued so far (warp-uniform call sites only; the loop
+    // bound is warp-uniform and the per-lane work a structured `if`, see
+    // profiles/r1_notes.md section 4)
+    auto maybe_flush = [&]() {
+      if (wh && added > (1u << 30) / sharers) {
+        for (int b = lane; b < nbins; b += 32) {
+          const unsigned int v = atomicExch(wh + b, 0u);
+          if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+        }
+        added = 0;
+      }
+    };
     auto drain = [&]() {
-      const unsigned int n = (qaddr - qbase) / Q_STRIDE;
+      __syncwarp();   // the group log was written by lane 0
+      const unsigned int n = (qaddr - qbase) >> 7;
       const unsigned int nmax = __reduce_max_sync(0xffffffffu, n);
       const float r2_low = fp->r2_low, inv_dr = fp->inv_dr, koff = fp->koff;
       for (unsigned int s = 0; s < nmax; ++s) {
         if (s < n) {
-          const float r2 = q_r2[s * TPB + tid];
+          const float r2 = q[s * 32 + lane];
           int k = __float2int_rd(__fmaf_rn(sqrt_approx(r2), inv_dr, koff));
           k = max(0, min(k, nbins - 1));
           const float2 t = __ldg(tab + k);
           bool ok = r2 >= r2_low;
           if (ok && !(r2 >= t.x && r2 < t.y)) {
-            const uint32_t jb = q_j[s * TPB + tid];
-            int rank = 0;
-            for (unsigned int e = 0; e < s; ++e)
-              rank += (q_j[e * TPB + tid] == jb &&
-                       __float_as_uint(q_r2[e * TPB + tid]) ==
-                           __float_as_uint(r2));
-            k = resolve_band<BOXKIND>(r2, jb, rank, xs, xi[0], xi[1], xi[2],
-                                      xi[3], yi[0], yi[1], yi[2], yi[3], zi[0],
-                                      zi[1], zi[2], zi[3], fp, &s_hp);
+            k = resolve_entry<BOXKIND>((int)s, lane, mark, glog, nlog, gi_cl,
+                                       np_i, gj_f, np_j, r2_cut, a.swapped, fp,
+                                       &s_hp);
             ++n_slow;
             ok = k >= 0;
           }
@@ -741,69 +1075,184 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
         }
       }
       qaddr = qbase;
+      nlog = 0;
+      // shared counters are 32-bit: flush this warp's copy long before wrap
+      added += 64u * nmax;
+      maybe_flush();
     };
 
-    if (!all_slow) {
+    // evaluate one staged j-group against my RI i-atoms
+    auto evaluate = [&](int packed, int slot) {
+      const int g = packed & 0xffffff, code = (packed >> 24) & 0x7f;
+      ++n_groups;
+      if (all_slow) {
+        // frame not provably safe for fp32: every pair through the fp64 path
+        const float *js = jst + slot * 3 * GJ;
+        for (int u = 0; u < GJ; ++u) {
+          // padding is excluded by index here: the reference arithmetic maps
+          // NaN to a distance in some box kinds
+          if (g * GJ + u >= a.n_j) break;
+          const float xj = js[u], yj = js[GJ + u], zj = js[2 * GJ + u];
 #pragma unroll 1
-      for (int j = 0; j < jcount; j += 4) {
-        const float4 X = *reinterpret_cast<const float4 *>(xs + j);
-        const float4 Y = *reinterpret_cast<const float4 *>(ys + j);
-        const float4 Z = *reinterpret_cast<const float4 *>(zs + j);
-        const float xj4[4] = {X.x, X.y, X.z, X.w};
-        const float yj4[4] = {Y.x, Y.y, Y.z, Y.w};
-        const float zj4[4] = {Z.x, Z.y, Z.z, Z.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
           for (int r = 0; r < RI; ++r) {
-            const float r2 = r2_fast<BOXKIND>(__fsub_rn(xj4[u], xi[r]),
-                                              __fsub_rn(yj4[u], yi[r]),
-                                              __fsub_rn(zj4[u], zi[r]), fb);
-            q_push(qaddr, r2, r2_cut, (uint32_t)j);
-          }
-          if ((u % Q_CHECK) == Q_CHECK - 1) {
-            // room for the next Q_CHECK*RI pushes in every lane?
-            if (__any_sync(0xffffffffu,
-                           qaddr > qbase + (QS - Q_CHECK * RI) * Q_STRIDE)) {
-              drain();
+            if (ic * CI + r * 32 + lane >= a.n_i) continue;
+            const float xi = gi_cl[r * 32 + lane], yi = gi_cl[np_i + r * 32 + lane],
+                        zi = gi_cl[2 * np_i + r * 32 + lane];
+            const int k = a.swapped
+                              ? exact_bin<BOXKIND>(xj, yj, zj, xi, yi, zi, fp, &s_hp)
+                              : exact_bin<BOXKIND>(xi, yi, zi, xj, yj, zj, fp, &s_hp);
+            ++n_slow;
+            if (k >= 0) {
+              if (wh) atomicAdd(wh + k, weight);
+              else atomicAdd(a.hist + k, (unsigned long long)weight);
             }
           }
         }
+        added += 2u * PAIRS_PER_GROUP * 32u;
+        maybe_flush();
+        return;
       }
-      drain();
-    } else {
-      // frame not provably safe for fp32: every pair through the fp64 path
-      for (int j = 0; j < jcount; ++j) {
-        const float xj = xs[j], yj = ys[j], zj = zs[j];
-#pragma unroll 1
-        for (int r = 0; r < RI; ++r) {
-          if (it * TILE + r * TPB + tid >= a.n1) continue;
-          const int k = exact_bin<BOXKIND>(xi[r], yi[r], zi[r], xj, yj, zj, fp,
-                                           &s_hp);
-          ++n_slow;
-          if (k >= 0) {
-            if (wh) atomicAdd(wh + k, weight);
-            else atomicAdd(a.hist + k, (unsigned long long)weight);
+      // room for one more group in every lane's queue and in the log?
+      if (nlog == LOGMAX ||
+          __any_sync(0xffffffffu,
+                     qaddr > qbase + (QS - PAIRS_PER_GROUP) * 128))
+        drain();
+      if (lane == 0) glog[nlog] = packed;
+      mark[nlog * 32 + lane] = (unsigned char)((qaddr - qbase) >> 7);
+      ++nlog;
+      if (code != cur_code) set_shift(code);
+      const float *js = jst + slot * 3 * GJ;
+      const float4 X0 = *reinterpret_cast<const float4 *>(js);
+      const float4 X1 = *reinterpret_cast<const float4 *>(js + 4);
+      const float4 Y0 = *reinterpret_cast<const float4 *>(js + GJ);
+      const float4 Y1 = *reinterpret_cast<const float4 *>(js + GJ + 4);
+      const float4 Z0 = *reinterpret_cast<const float4 *>(js + 2 * GJ);
+      const float4 Z1 = *reinterpret_cast<const float4 *>(js + 2 * GJ + 4);
+      const float xj8[GJ] = {X0.x, X0.y, X0.z, X0.w, X1.x, X1.y, X1.z, X1.w};
+      const float yj8[GJ] = {Y0.x, Y0.y, Y0.z, Y0.w, Y1.x, Y1.y, Y1.z, Y1.w};
+      const float zj8[GJ] = {Z0.x, Z0.y, Z0.z, Z0.w, Z1.x, Z1.y, Z1.z, Z1.w};
+      if ((BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN)) {
+#pragma unroll
+        for (int u = 0; u < GJ; ++u)
+#pragma unroll
+          for (int r = 0; r < RI; ++r)
+            q_push(qaddr,
+                   pair_r2<BOXKIND, true>(xj8[u], yj8[u], zj8[u], xs[r], ys[r],
+                                          zs[r], fb),
+                   r2_cut);
+      } else {
+#pragma unroll
+        for (int u = 0; u < GJ; ++u)
+#pragma unroll
+          for (int r = 0; r < RI; ++r)
+            q_push(qaddr,
+                   pair_r2<BOXKIND, false>(xj8[u], yj8[u], zj8[u], xs[r], ys[r],
+                                           zs[r], fb),
+                   r2_cut);
+      }
+    };
+
+    // cp.async pipeline: the copy of the newest group flies while the
+    // previous one is evaluated
+    int pend = -1, pend_slot = 0, next_slot = 0;
+    auto on_hit = [&](int packed) {
+      const int g = packed & 0xffffff;
+      __syncwarp();   // every lane is done reading the slot being refilled
+      if (lane < 6) {
+        const int plane = lane >> 1, half = lane & 1;
+        cp_async16(jst + next_slot * 3 * GJ + plane * GJ + half * 4,
+                   gj_f + (size_t)plane * np_j + (size_t)g * GJ + half * 4);
+      }
+      cp_async_commit();
+      if (pend >= 0) {
+        cp_async_wait<1>();
+        __syncwarp();
+        evaluate(pend, pend_slot);
+      }
+      pend = packed;
+      pend_slot = next_slot;
+      next_slot ^= 1;
+    };
+    auto finish = [&]() {
+      if (pend >= 0) {
+        cp_async_wait<0>();
+        __syncwarp();
+        evaluate(pend, pend_slot);
+        pend = -1;
+      }
+      if (!all_slow) drain();
+    };
+
+    // test `count` consecutive j-groups starting at gstart (index wraps)
+    auto scan_groups = [&](int gstart, int count) {
+      const float *gb = a.gbb + (size_t)f * 6 * a.ngrp_j;
+      for (int base = 0; base < count; base += 32) {
+        const int t = base + lane;
+        int g = gstart + t;
+        if (g >= a.ngrp_j) g -= a.ngrp_j;
+        bool pass = false;
+        int code = CODE_ZERO;
+        if (t < count) {
+          float gap[3];
+          bool valid = true;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float cj = gb[(size_t)k * a.ngrp_j + g];
+            const float hs = __fadd_rn(ch[k], gb[(size_t)(3 + k) * a.ngrp_j + g]);
+            const float D = __fsub_rn(cj, cc[k]);
+            float d = fabsf(D);
+            d = fminf(d, __fsub_rn(per[k], d));
+            gap[k] = __fmul_rn(fmaxf(0.f, __fsub_rn(d, hs)), wk[k]);
+            if (BOXKIND == RDFK_BOX_ORTHO) {
+              // lattice shift of this (cluster, group) along k and whether it
+              // is the minimum image of every pair that can be in range
+              const float hp_ = __fmul_rn(0.5f, per[k]);
+              const int n = (D > hp_) ? 1 : ((D < -hp_) ? -1 : 0);
+              const float Dn = fabsf(__fsub_rn(D, __fmul_rn((float)n, per[k])));
+              if (per[k] < INFINITY) {
+                valid = valid && (__fadd_rn(__fadd_rn(Dn, hs), rshift) < per[k]);
+                code += n * (1 << (2 * k));
+              }
+            }
           }
+          if (BOXKIND == RDFK_BOX_TRI)
+            pass = fmaxf(gap[0], fmaxf(gap[1], gap[2])) <= rprune;
+          else
+            pass = __fmaf_rn(gap[2], gap[2],
+                             __fmaf_rn(gap[1], gap[1], __fmul_rn(gap[0], gap[0])))
+                   <= __fmul_rn(rprune, rprune);
+          if (BOXKIND == RDFK_BOX_NONE) code = CODE_ZERO | CODE_PLAIN;
+          else if (BOXKIND == RDFK_BOX_ORTHO && shift_ok && valid)
+            code |= CODE_PLAIN;
+          else code = CODE_ZERO;
+        }
+        unsigned int m = __ballot_sync(0xffffffffu, pass);
+        const int packed = g | (code << 24);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          on_hit(__shfl_sync(0xffffffffu, packed, b));
         }
       }
+      finish();
+    };
+
+    if (a.symmetric) {
+      // own cluster in full (weight 1: both orders and the self pairs are
+      // evaluated), then the circulant half of the other clusters (weight 2)
+      weight = 1u;
+      scan_groups(ic * GPC, GPC);
+      const int nt = a.ncl_i;
+      int cnt = (nt - 1) / 2;
+      if ((nt & 1) == 0 && ic < nt / 2) ++cnt;
+      weight = 2u;
+      int gs = (ic + 1) * GPC;
+      if (gs >= a.ngrp_j) gs -= a.ngrp_j;
+      if (cnt > 0) scan_groups(gs, cnt * GPC);
+    } else {
+      weight = 1u;
+      scan_groups(0, a.ngrp_j);
     }
-    ++n_items;
-    // shared counters are 32-bit: flush long before they can wrap
-    if (copies && (n_items % a.flush_every) == 0u) {
-      __syncthreads();
-      for (int b = tid; b < nbins; b += TPB) {
-        unsigned long long s = 0;
-        for (int c = 0; c < copies; ++c) {
-          s += hist_s[(size_t)c * nbins + b];
-          hist_s[(size_t)c * nbins + b] = 0u;
-        }
-        if (s) atomicAdd(a.hist + b, s);
-      }
-    }
-    __syncthreads();  // everyone is done with jbuf[buf] and saw s_next
-    buf ^= 1;
-    cur = s_next[buf];
   }
 
   __syncthreads();
@@ -818,11 +1267,12 @@ __global__ __launch_bounds__(TPB, 2) void pair_tile_kernel(const PairArgs a) {
   unsigned int tot = n_slow;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if ((tid & 31) == 0 && tot) atomicAdd(&a.header->stats[0], (unsigned long long)tot);
-  if (tid == 0 && n_items) {
-    atomicAdd(&a.header->stats[2], (unsigned long long)n_items);
-    atomicAdd(&a.header->stats[3],
-              (unsigned long long)n_items * TILE * (unsigned long long)TILE);
+  if (lane == 0) {
+    if (tot) atomicAdd(&a.header->stats[0], (unsigned long long)tot);
+    if (n_items) atomicAdd(&a.header->stats[2], (unsigned long long)n_items);
+    if (n_groups)
+      atomicAdd(&a.header->stats[3],
+                (unsigned long long)n_groups * (unsigned long long)(CI * GJ));
   }
 }
 
@@ -1017,6 +1467,25 @@ extern "C" size_t rdfk_rdf_workspace_bytes(int F, int n1, int n2, int nbins,
 }
 
 template <int BOXKIND>
+static int sort_side(const float *staged, int n, int np, int bits, int F,
+                     const FrameParams *fparams, uint32_t *keys,
+                     uint32_t *lrank, uint32_t *cells, float *sorted,
+                     float *gbb, float *cbb, cudaStream_t st) {
+  const size_t ncell = (size_t)1 << (3 * bits);
+  CUDA_TRY(cudaMemsetAsync(cells, 0, sizeof(uint32_t) * ncell * (size_t)F, st));
+  key_kernel<BOXKIND><<<dim3((n + 255) / 256, F), 256, 0, st>>>(
+      staged, n, np, fparams, bits, keys, lrank, cells);
+  scan_kernel<<<F, 1024, 0, st>>>(cells, (int)ncell);
+  scatter_kernel<<<dim3(np / 256 + 1, F), 256, 0, st>>>(staged, n, np, bits,
+                                                        keys, lrank, cells,
+                                                        sorted);
+  bbox_kernel<BOXKIND><<<dim3((np / GJ + 255) / 256, F), 256, 0, st>>>(
+      sorted, np, fparams, gbb, cbb);
+  COUNT_LAUNCH(4);
+  return RDFK_OK;
+}
+
+template <int BOXKIND>
 static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
                       int n1, const int *idx2, int n2, int same_group,
                       const float *box, const HistParams &hp, int excl_a,
@@ -1028,30 +1497,60 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   float2 *tables = reinterpret_cast<float2 *>(ws + L.tables);
   float *g1 = reinterpret_cast<float *>(ws + L.g1);
   float *g2 = reinterpret_cast<float *>(ws + L.g2);
+  float *s1 = reinterpret_cast<float *>(ws + L.s1);
+  float *s2 = reinterpret_cast<float *>(ws + L.s2);
+  float *gbb1 = reinterpret_cast<float *>(ws + L.gbb1);
+  float *gbb2 = reinterpret_cast<float *>(ws + L.gbb2);
+  float *cbb1 = reinterpret_cast<float *>(ws + L.cbb1);
+  float *cbb2 = reinterpret_cast<float *>(ws + L.cbb2);
+  uint32_t *keys = reinterpret_cast<uint32_t *>(ws + L.keys);
+  uint32_t *lrank = reinterpret_cast<uint32_t *>(ws + L.lrank);
+  uint32_t *cells = reinterpret_cast<uint32_t *>(ws + L.cells);
 
   init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(header, extents, F);
   COUNT_LAUNCH(same_group ? 3 : 4);  // init + stage(s) + tables
-  stage_kernel<BOXKIND><<<dim3(L.np1 / 256, F), 256, 0, st>>>(
+  stage_kernel<BOXKIND><<<dim3((L.np1 + 255) / 256, F), 256, 0, st>>>(
       xyz, natoms, idx1, n1, L.np1, box, g1, extents);
   if (!same_group)
-    stage_kernel<BOXKIND><<<dim3(L.np2 / 256, F), 256, 0, st>>>(
+    stage_kernel<BOXKIND><<<dim3((L.np2 + 255) / 256, F), 256, 0, st>>>(
         xyz, natoms, idx2, n2, L.np2, box, g2, extents);
-  tables_kernel<<<F, 256, 0, st>>>(BOXKIND, box, extents, hp, fparams, tables);
+  // RDFK_DEBUG: bit 0 = no pruning (every group is evaluated), bit 1 = no
+  // shifted variant.  Results must not depend on either (tests/).
+  int debug_flags = 0;
+  if (const char *dbg = getenv("RDFK_DEBUG")) debug_flags = atoi(dbg);
+  tables_kernel<<<F, 256, 0, st>>>(BOXKIND, box, extents, hp, debug_flags,
+                                   fparams, tables);
 
-  PairArgs a;
-  a.g1 = g1; a.g2 = g2;
-  a.np1 = L.np1; a.np2 = L.np2; a.n1 = n1; a.n2 = n2; a.F = F;
-  a.nt1 = L.np1 / TILE; a.nt2 = L.np2 / TILE;
-  a.symmetric = same_group ? 1 : 0;
-  if (a.symmetric) {
-    const long long nt = a.nt1, B = (nt - 1) / 2 + 1;
-    a.items_per_frame = (int)(nt * B + ((nt % 2 == 0) ? nt / 2 : 0));
-  } else {
-    a.items_per_frame = a.nt1 * a.nt2;
+  int rc = sort_side<BOXKIND>(g1, n1, L.np1, L.bits1, F, fparams, keys, lrank,
+                              cells, s1, gbb1, cbb1, st);
+  if (rc) return rc;
+  if (!same_group) {
+    rc = sort_side<BOXKIND>(g2, n2, L.np2, L.bits2, F, fparams, keys, lrank,
+                            cells, s2, gbb2, cbb2, st);
+    if (rc) return rc;
   }
-  const long long total = (long long)a.items_per_frame * F;
+
+  // the larger group supplies the work items (clusters), the other the groups
+  const bool swap = !same_group && n2 > n1;
+  PairArgs a;
+  a.gi = swap ? s2 : s1;
+  a.gj = swap ? s1 : s2;
+  a.cbb = swap ? cbb2 : cbb1;
+  a.gbb = swap ? gbb1 : gbb2;
+  a.np_i = swap ? L.np2 : L.np1;
+  a.np_j = swap ? L.np1 : L.np2;
+  a.n_i = swap ? n2 : n1;
+  a.n_j = swap ? n1 : n2;
+  a.F = F;
+  a.ncl_i = a.np_i / CI;
+  a.ngrp_j = a.np_j / GJ;
+  a.symmetric = same_group ? 1 : 0;
+  a.swapped = swap ? 1 : 0;
+  if (a.ngrp_j >= (1 << 24))
+    return set_err(RDFK_EINVAL, "group too large (max 134e6 atoms)%s%s");
+  const long long total = (long long)a.ncl_i * F;
   if (total > 0x7fff0000LL)
-    return set_err(RDFK_EINVAL, "too many tile work items in one call; "
+    return set_err(RDFK_EINVAL, "too many cluster work items in one call; "
                                 "pass fewer frames%s%s");
   a.total_items = (int)total;
   a.fparams = fparams; a.tables = tables; a.hp = hp; a.hist = hist;
@@ -1060,26 +1559,19 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   int copies = (int)(HIST_SMEM_BUDGET / per_copy);
   if (copies > NWARP) copies = NWARP;
   a.hist_copies = copies;
-  {
-    // one item adds at most 32*RI*TILE*2 to a warp's copy; several warps may
-    // share a copy when nbins is large
-    const unsigned int sharers = copies ? (NWARP + copies - 1) / copies : 1;
-    a.flush_every = (1u << 31) / (32u * RI * TILE * 2u * sharers);
-    if (a.flush_every < 1u) a.flush_every = 1u;
-  }
-  const size_t smem = 2 * 3 * TILE * sizeof(float) + 2 * (size_t)QS * TPB * 4 +
-                      (size_t)copies * per_copy;
-  CUDA_TRY(cudaFuncSetAttribute(pair_tile_kernel<BOXKIND>,
+  const size_t smem = (size_t)NWARP * SM_WARP + (size_t)copies * per_copy;
+  CUDA_TRY(cudaFuncSetAttribute(pair_prune_kernel<BOXKIND>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   int occ = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, pair_tile_kernel<BOXKIND>, TPB, smem));
-  if (occ < 1) return set_err(RDFK_ECUDA, "pair_tile_kernel does not fit%s%s");
+      &occ, pair_prune_kernel<BOXKIND>, TPB, smem));
+  if (occ < 1) return set_err(RDFK_ECUDA, "pair_prune_kernel does not fit%s%s");
   long long grid = (long long)sms * occ;
-  if (grid > total) grid = total;
+  const long long need = (total + NWARP - 1) / NWARP;
+  if (grid > need) grid = need;
   if (grid > 0) {
-    pair_tile_kernel<BOXKIND><<<(int)grid, TPB, smem, st>>>(a);
+    pair_prune_kernel<BOXKIND><<<(int)grid, TPB, smem, st>>>(a);
     COUNT_LAUNCH(1);
   }
 
