@@ -1,0 +1,208 @@
+"""GPU parity for the sorted / pruned pair kernel: everything the spatial sort,
+the box tests and the one-shift-per-group fast path could get wrong must still
+give the oracle's integers.  RDFK_DEBUG (bit 0: no pruning, bit 1: no shifted
+variant) is read by librdfk on every call; results must not depend on it."""
+import os
+
+import numpy as np
+import pytest
+
+from pmda_b200 import synthetic
+from pmda_b200.rdf import InterRDF
+from pmda_b200.universe import Universe
+
+from helpers import oracle_interrdf
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(u, g1, g2, nbins=75, rng=(0.0, 15.0), excl=None, debug=None):
+    old = os.environ.pop("RDFK_DEBUG", None)
+    try:
+        if debug is not None:
+            os.environ["RDFK_DEBUG"] = str(debug)
+        r = InterRDF(g1, g2, nbins=nbins, range=rng, exclusion_block=excl)
+        r.run()
+        return r.count.copy()
+    finally:
+        os.environ.pop("RDFK_DEBUG", None)
+        if old is not None:
+            os.environ["RDFK_DEBUG"] = old
+
+
+def _check_all_modes(u, g1, g2, nbins=75, rng=(0.0, 15.0), excl=None):
+    want, _, _ = oracle_interrdf(u, g1, g2, nbins, rng, excl)
+    for debug in (None, 1, 2, 3):
+        got = _gpu(u, g1, g2, nbins, rng, excl, debug)
+        np.testing.assert_array_equal(got, want, err_msg="RDFK_DEBUG=%r" % debug)
+    return want
+
+
+def test_midsize_ortho_all_modes():
+    # big enough that most group pairs are pruned and most of the rest shifted
+    rng = np.random.default_rng(101)
+    L = np.array([62.0, 58.0, 66.0])
+    pos = (rng.random((2, 20000, 3)) * L).astype(np.float32)
+    u = Universe(pos, list(L) + [90, 90, 90])
+    want = _check_all_modes(u, u.atoms, u.atoms, nbins=200)
+    assert want[0] >= 2 * 20000
+
+
+def test_two_groups_swapped_roles_all_modes():
+    rng = np.random.default_rng(102)
+    L = 55.0
+    pos = (rng.random((2, 9000, 3)) * L).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    perm = rng.permutation(9000)
+    small, large = u.atoms[np.sort(perm[:500])], u.atoms[np.sort(perm[500:])]
+    _check_all_modes(u, small, large)          # i side = g2 (swapped)
+    _check_all_modes(u, large, small)          # i side = g1
+
+
+def test_centered_box_negative_coordinates():
+    # coordinates in [-L/2, L/2): the wrap origin is the frame minimum
+    rng = np.random.default_rng(103)
+    L = 48.0
+    pos = ((rng.random((2, 6000, 3)) - 0.5) * L).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 12.0))
+
+
+def test_slightly_unwrapped_and_far_unwrapped():
+    rng = np.random.default_rng(104)
+    L = 40.0
+    pos = (rng.random((2, 4000, 3)) * L).astype(np.float32)
+    pos[0, :50] += np.float32(L)            # a few atoms one image away
+    pos[1, 100:130] -= np.float32(3 * L)    # and three images away
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 10.0))
+
+
+def test_cutoff_larger_than_half_box():
+    rng = np.random.default_rng(105)
+    L = np.array([22.0, 26.0, 24.0])
+    pos = (rng.random((2, 1500, 3)) * L).astype(np.float32)
+    u = Universe(pos, list(L) + [90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 15.0))
+
+
+def test_clustered_density_with_vacuum():
+    # blobs + slab: many empty cells, very uneven cluster extents
+    rng = np.random.default_rng(106)
+    L = np.array([80.0, 80.0, 120.0])
+    n = 8000
+    centres = rng.random((12, 3)) * L
+    blob = centres[rng.integers(0, 12, n // 2)] + rng.normal(0, 3.0, (n // 2, 3))
+    slab = rng.random((n - n // 2, 3)) * L
+    slab[:, 2] = 60.0 + rng.normal(0, 4.0, n - n // 2)
+    p = np.mod(np.concatenate([blob, slab]), L)
+    pos = np.stack([p, np.mod(p + rng.normal(0, 0.5, p.shape), L)]).astype(np.float32)
+    pos = np.minimum(pos, np.nextafter(L.astype(np.float32), np.float32(0)))
+    u = Universe(pos, list(L) + [90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, nbins=100)
+    _check_all_modes(u, u.atoms[:1000], u.atoms[4000:], nbins=100)
+
+
+def test_all_atoms_identical_and_tiny_groups():
+    L = 30.0
+    pos = np.full((1, 300, 3), 7.25, dtype=np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    want = _check_all_modes(u, u.atoms, u.atoms)
+    assert want[0] == 300 * 300
+    rng = np.random.default_rng(107)
+    pos = (rng.random((3, 40, 3)) * L).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    _check_all_modes(u, u.atoms[:1], u.atoms[1:])
+    _check_all_modes(u, u.atoms[:7], u.atoms[5:9])
+
+
+def test_no_box_clustered_all_modes():
+    rng = np.random.default_rng(108)
+    pos = np.concatenate([rng.normal(0, 6, (1, 3000, 3)),
+                          rng.normal(40, 6, (1, 3000, 3))], axis=1)
+    u = Universe(pos.astype(np.float32), None)
+    _check_all_modes(u, u.atoms, u.atoms)
+    _check_all_modes(u, u.atoms[:3000], u.atoms[3000:], rng=(20.0, 90.0))
+
+
+def test_partial_pbc_all_modes():
+    rng = np.random.default_rng(109)
+    pos = (rng.random((2, 5000, 3)) * [50, 50, 90]).astype(np.float32)
+    u = Universe(pos, [50.0, 50.0, 0.0, 90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms)
+
+
+@pytest.mark.parametrize("dims", [
+    [60.0, 62.0, 64.0, 80.0, 75.0, 70.0],
+    [70.0, 70.0, 70.0, 60.0, 60.0, 90.0],
+])
+def test_triclinic_midsize_all_modes(dims):
+    rng = np.random.default_rng(110)
+    pos = synthetic.uniform_triclinic(2, 12000, dims, rng)
+    u = Universe(pos, dims)
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 12.0))
+    _check_all_modes(u, u.atoms[:300], u.atoms[300:], rng=(0.0, 12.0))
+
+
+def test_triclinic_exact_frames_all_modes():
+    # cut-off beyond the brick: every evaluated pair on the fp64 path
+    dims = [24.0, 26.0, 28.0, 70.0, 80.0, 65.0]
+    rng = np.random.default_rng(111)
+    pos = synthetic.uniform_triclinic(1, 700, dims, rng)
+    u = Universe(pos, dims)
+    _check_all_modes(u, u.atoms, u.atoms)
+    _check_all_modes(u, u.atoms[:100], u.atoms[90:])
+
+
+def test_nonfinite_coordinates_match_oracle():
+    rng = np.random.default_rng(112)
+    L = 30.0
+    pos = (rng.random((2, 900, 3)) * L).astype(np.float32)
+    pos[0, 17, 1] = np.nan
+    pos[1, 400, 0] = np.inf
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms)
+    dims = [40.0, 42.0, 44.0, 80.0, 75.0, 70.0]
+    pos = synthetic.uniform_triclinic(1, 600, dims, rng)
+    pos[0, 5, 2] = np.nan
+    u = Universe(pos, dims)
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 12.0))
+
+
+def test_large_nbins_global_atomics_and_shared_copies():
+    rng = np.random.default_rng(113)
+    L = 36.0
+    pos = (rng.random((1, 3000, 3)) * L).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    for nbins in (3000, 9000):
+        _check_all_modes(u, u.atoms, u.atoms, nbins=nbins, rng=(0.5, 14.0))
+
+
+def test_box_changes_every_frame():
+    rng = np.random.default_rng(114)
+    F, n = 5, 5000
+    Ls = 50.0 + rng.random((F, 3)) * 4.0
+    pos = (rng.random((F, n, 3)) * Ls[:, None, :]).astype(np.float32)
+    dims = np.concatenate([Ls, np.full((F, 3), 90.0)], axis=1).astype(np.float32)
+    u = Universe(pos, dims)
+    _check_all_modes(u, u.atoms, u.atoms)
+
+
+def test_exclusion_block_with_sorted_atoms():
+    rng = np.random.default_rng(115)
+    L = 45.0
+    pos = (rng.random((2, 6000, 3)) * L).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, excl=(3, 3))
+    _check_all_modes(u, u.atoms[:2000], u.atoms[2000:], excl=(2, 4))
+
+
+def test_lattice_on_edges_all_modes():
+    m, a = 16, 1.5
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"),
+                 axis=-1).reshape(-1, 3)
+    pos = (g * a).astype(np.float32)[None]
+    L = m * a
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, nbins=20, rng=(0.0, 6.0))
+    _check_all_modes(u, u.atoms, u.atoms, nbins=30, rng=(0.0, 9.0))
