@@ -83,7 +83,6 @@ constexpr int CI = 32 * RI;      // atoms per i-cluster (one warp work item)
 constexpr int GJ = 8;            // atoms per j-group (pruning granule)
 constexpr int GPC = CI / GJ;     // j-groups per cluster
 constexpr int TILE = CI;         // padding granule of the staged arrays
-constexpr int HIST_SMEM_BUDGET = 32 * 1024;  // bytes for warp-private copies
 constexpr float MAGIC = 12582912.0f;         // 1.5 * 2^23: rint via add/sub
 constexpr double EPS32 = 5.9604644775390625e-8;  // 2^-24
 
@@ -94,10 +93,12 @@ struct FrameParams {
   float finv[3];  // fast path inverse, 0 when the axis has no PBC
   float tri[9];   // triclinic vectors, row-major (a; b; c)
   float tinv[3];  // fast path 1/ax, 1/by, 1/cz
-  float r2_cut;   // fp32 r2 >= r2_cut  => reference distance > r1 for sure
-  float r2_low;   // fp32 r2 <  r2_low  => reference distance < r0 for sure
-  float inv_dr;   // nbins / (r1 - r0)
-  float koff;     // -r0 * inv_dr
+  // two decision tables per frame: [0] "tight" for pairs evaluated without any
+  // lattice shift (fp32 dx is the reference's own float difference), [1]
+  // "loose" for shifted / per-pair minimum-image arithmetic
+  float r2_cut[2];  // fp32 r2 >= r2_cut  => reference distance > r1 for sure
+  float inv_dr;     // nbins / (r1 - r0)
+  float koffm;      // -r0 * inv_dr - 0.5 (then + 1.5 * 2^23: nearest = floor)
   int all_slow;   // fast path not provably safe for this frame
   // sorting / pruning.  "prune space" u: ortho and no-box = Cartesian offset
   // from `org`, wrapped into [0, L) on periodic axes; triclinic = fractional
@@ -151,7 +152,7 @@ static WsLayout ws_layout(int F, int n1, int n2, int nbins, int same_group) {
   w.fparams = off;
   off = align_up(off + sizeof(FrameParams) * (size_t)F, 256);
   w.tables = off;
-  off = align_up(off + sizeof(float2) * (size_t)nbins * (size_t)F, 256);
+  off = align_up(off + sizeof(float2) * 2 * ((size_t)nbins + 1) * (size_t)F, 256);
   w.g1 = off;
   off = align_up(off + sizeof(float) * 3 * (size_t)w.np1 * (size_t)F, 256);
   w.g2 = same_group ? w.g1 : off;
@@ -433,7 +434,7 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
                               FrameParams *__restrict__ fparams,
                               float2 *__restrict__ tables) {
   const int f = blockIdx.x;
-  __shared__ double s_delta;
+  __shared__ double s_delta[2];
   __shared__ int s_slow;
   FrameParams *fp = fparams + f;
   if (threadIdx.x == 0) {
@@ -563,11 +564,23 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
     const double delta = sqrt(dk[0] * dk[0] + dk[1] * dk[1] + dk[2] * dk[2]);
     if (!(delta < 1e30)) slow = true;
     if (slow) shift_ok = false;
-    s_delta = delta;
+    // tight table: no shift, n = 0 on every axis.  fp32 dx equals the
+    // reference's float difference; the reference then multiplies by
+    // L * (float)(1/L) = 1 + c, |c| <= 2^-24, so the components differ by at
+    // most eps |dx| <= eps R.  Without a box they are identical.
+    double dt[3] = {0.0, 0.0, 0.0};
+    if (boxkind == RDFK_BOX_ORTHO)
+      for (int k = 0; k < 3; ++k)
+        if (fp->fl[k] > 0.f) dt[k] = EPS32 * R * 1.01;
+    s_delta[0] = (boxkind == RDFK_BOX_TRI)
+                     ? delta
+                     : sqrt(dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2]);
+    s_delta[1] = delta;
     s_slow = slow ? 1 : 0;
     fp->all_slow = slow ? 1 : 0;
-    fp->inv_dr = (float)((double)hp.nbins / (hp.r1 - hp.r0));
-    fp->koff = (float)(-hp.r0 * ((double)hp.nbins / (hp.r1 - hp.r0)));
+    const double inv_dr = (double)hp.nbins / (hp.r1 - hp.r0);
+    fp->inv_dr = (float)inv_dr;
+    fp->koffm = (float)(-hp.r0 * inv_dr - 0.5);
     fp->rprune = (float)((rmax + slack) * (1.0 + 1e-6));
     fp->rshift = (float)((R + 8.0 * delta) * (1.0 + 1e-6));
     if (shift_ok)
@@ -578,34 +591,42 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
     fp->prune_ok = (finite && slack < 1e15 && !(debug_flags & 1)) ? 1 : 0;
   }
   __syncthreads();
-  const double delta = s_delta;
   const double gam = 3.5 * EPS32;
-  // T_hi(e): fp32 r2 >= T_hi  =>  reference d >= e (and > e)
-  // T_lo(e): fp32 r2 <  T_lo  =>  reference d <  e
-  auto t_hi = [&](double e) -> float {
-    const double dp = delta * 1.001 + 1e-15 * fabs(e) + 1e-300;
-    const double v = (e + dp) * (e + dp) * (1.0 + gam);
-    return nextafterf(__double2float_ru(v), INFINITY);
-  };
-  auto t_lo = [&](double e) -> float {
-    const double dp = delta * 1.001 + 1e-15 * fabs(e) + 1e-300;
-    const double m = e - dp;
-    if (!(m > 0.0)) return 0.f;
-    const double v = m * m * (1.0 - gam);
-    const float r = nextafterf(__double2float_rd(v), 0.f);
-    return r > 0.f ? r : 0.f;
-  };
   const int nbins = hp.nbins;
-  for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
-    const double e0 = hp.edges[k], e1 = hp.edges[k + 1];
-    float lo = (k == 0 && e0 <= 0.0) ? -INFINITY : t_hi(e0);
-    float hi = t_lo(e1);
-    if (s_slow) { lo = INFINITY; hi = 0.f; }
-    tables[(size_t)f * nbins + k] = make_float2(lo, hi);
-  }
-  if (threadIdx.x == 0) {
-    fp->r2_cut = s_slow ? INFINITY : t_hi(hp.edges[nbins]);
-    fp->r2_low = (hp.edges[0] > 0.0 && !s_slow) ? t_lo(hp.edges[0]) : 0.f;
+  for (int w = 0; w < 2; ++w) {
+    const double delta = s_delta[w];
+    // T_hi(e): fp32 r2 >= T_hi  =>  reference d >= e (and > e)
+    // T_lo(e): fp32 r2 <  T_lo  =>  reference d <  e
+    auto t_hi = [&](double e) -> float {
+      const double dp = delta * 1.001 + 1e-15 * fabs(e) + 1e-300;
+      const double v = (e + dp) * (e + dp) * (1.0 + gam);
+      return nextafterf(__double2float_ru(v), INFINITY);
+    };
+    auto t_lo = [&](double e) -> float {
+      const double dp = delta * 1.001 + 1e-15 * fabs(e) + 1e-300;
+      const double m = e - dp;
+      if (!(m > 0.0)) return 0.f;
+      const double v = m * m * (1.0 - gam);
+      const float r = nextafterf(__double2float_rd(v), 0.f);
+      return r > 0.f ? r : 0.f;
+    };
+    // entry k + 1 decides bin k; entry 0 is "certainly below r0: drop"
+    float2 *tab = tables + ((size_t)f * 2 + w) * (nbins + 1);
+    for (int k = threadIdx.x; k <= nbins; k += blockDim.x) {
+      float lo, hi;
+      if (k == 0) {
+        lo = -INFINITY;
+        hi = hp.edges[0] > 0.0 ? t_lo(hp.edges[0]) : 0.f;
+      } else {
+        const double e0 = hp.edges[k - 1], e1 = hp.edges[k];
+        lo = (k == 1 && e0 <= 0.0) ? -INFINITY : t_hi(e0);
+        hi = t_lo(e1);
+      }
+      if (s_slow) { lo = INFINITY; hi = 0.f; }
+      tab[k] = make_float2(lo, hi);
+    }
+    if (threadIdx.x == 0)
+      fp->r2_cut[w] = s_slow ? INFINITY : t_hi(hp.edges[nbins]);
   }
 }
 
@@ -821,20 +842,21 @@ __global__ __launch_bounds__(256) void bbox_kernel(
 }
 
 struct PairArgs {
-  const float *gi;   // sorted [F][3][np_i]: the side whose clusters are work items
-  const float *gj;   // sorted [F][3][np_j]
-  const float *cbb;  // cluster boxes of the i side [F][6][ncl_i]
-  const float *gbb;  // group boxes of the j side   [F][6][ngrp_j]
+  const float *gi;    // sorted [F][3][np_i]: the side whose clusters are work items
+  const float *gj;    // sorted [F][3][np_j]
+  const float *cbbi;  // cluster boxes of the i side [F][6][ncl_i]
+  const float *cbbj;  // cluster boxes of the j side [F][6][ncl_j]
+  const float *gbbj;  // group boxes of the j side   [F][6][ngrp_j]
   int np_i, np_j, F;
-  int n_i, n_j;      // real atoms (the sorted arrays hold them first)
-  int ncl_i, ngrp_j;
-  int symmetric;     // gi == gj: circulant half of the cluster matrix
-  int swapped;       // i side is the reference's g2 (`conf`), j side its g1
-  int total_items;   // F * ncl_i
+  int n_i, n_j;       // real atoms (the sorted arrays hold them first)
+  int ncl_i, ncl_j, ngrp_j;
+  int symmetric;      // gi == gj: circulant half of the cluster matrix
+  int swapped;        // i side is the reference's g2 (`conf`), j side its g1
+  int total_items;    // F * ncl_i
   const FrameParams *fparams;
-  const float2 *tables;
+  const float2 *tables;   // [F][2][nbins + 1]
   HistParams hp;
-  int hist_copies;   // warp-private shared copies (0 = global atomics)
+  int hist_copies;    // warp-private shared copies (0 = global atomics)
   unsigned long long *hist;
   WsHeader *header;
 };
@@ -844,24 +866,29 @@ struct PairArgs {
 // them where they are found wastes the warp on divergence (measured 2.8x
 // slower, tools/ubench2.cu).  Instead every lane appends the fp32 r2 of its
 // hits to a private queue in shared memory with three predicated instructions
-// (no branch), and the warp drains all queues at warp-uniform points.  The
-// pair behind an entry is implied: the warp logs the j-groups it evaluated
-// since the last drain and every lane marks its queue length at each group
-// start, so the rare band failure re-scans one group (resolve_entry).
+// (no branch), and the warp drains all queues at warp-uniform points, four
+// entries per lane in flight.  The sign bit of an entry selects the decision
+// table (negative: shifted / minimum-image arithmetic).  The pair behind an
+// entry is implied: the warp logs the j-groups it evaluated since the last
+// drain and every lane marks its queue length at each group start, so the
+// rare band failure re-scans one group (resolve_entry).
 // ---------------------------------------------------------------------------
 constexpr int QS = 64;        // queue slots per lane
 constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
-constexpr int NST = 2;        // cp.async staging slots per warp
+constexpr int NSTAGE = 32;    // staged j-groups per warp (one test round)
 constexpr int PAIRS_PER_GROUP = GJ * RI;   // per lane
 static_assert(QS >= 2 * PAIRS_PER_GROUP, "queue must absorb one group");
-static_assert(QS < 256, "marks are bytes");
+static_assert(QS < 256 && QS % 4 == 0, "marks are bytes; drain is 4-wide");
 
 constexpr int SM_Q = QS * 32 * 4;              // bytes per warp: queue
-constexpr int SM_ST = NST * 3 * GJ * 4;        // staging ring
+constexpr int SM_ST = NSTAGE * 3 * GJ * 4;     // staged j-groups
+constexpr int SM_CODE = NSTAGE * 4;            // their (group, code) words
 constexpr int SM_LOG = LOGMAX * 4;             // group log
 constexpr int SM_MARK = LOGMAX * 32;           // queue marks (bytes)
-constexpr int SM_WARP = SM_Q + SM_ST + SM_LOG + SM_MARK;
+constexpr int SM_WARP = SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK;
+constexpr int SM_FIXED = NWARP * SM_WARP;
 
+// hit <=> r2 < cut.  NEG variants queue -r2 (hit <=> -r2 > -cut).
 __device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut) {
   asm volatile(
       "{\n"
@@ -874,18 +901,27 @@ __device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut) {
       : "f"(r2), "f"(cut)
       : "memory");
 }
+__device__ __forceinline__ void q_push_neg(uint32_t &qaddr, float r2n,
+                                           float ncut) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.gt.f32 p, %1, %2;\n"
+      "@p st.shared.f32 [%0], %1;\n"
+      "@p add.u32 %0, %0, 128;\n"
+      "}\n"
+      : "+r"(qaddr)
+      : "f"(r2n), "f"(ncut)
+      : "memory");
+}
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
                "l"(src)
                : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // group code: bits 0-1 nx+1, 2-3 ny+1, 4-5 nz+1, bit 6 = one shift is valid
@@ -897,16 +933,29 @@ __device__ __forceinline__ void decode_shift(int code, const FastBox &fb,
 }
 constexpr int CODE_PLAIN = 64;
 constexpr int CODE_ZERO = 1 | (1 << 2) | (1 << 4);
+// which arithmetic a group code selects
+//   0: plain, no shift  -> +r2, tight table
+//   1: plain, shifted   -> -r2, loose table
+//   2: per-pair minimum image (ortho generic / triclinic brick) -> -r2, loose
+template <int BOXKIND>
+__device__ __forceinline__ int code_variant(int code) {
+  if (BOXKIND == RDFK_BOX_NONE) return 0;
+  if (BOXKIND == RDFK_BOX_TRI) return 2;
+  if (!(code & CODE_PLAIN)) return 2;
+  return (code & 63) == CODE_ZERO ? 0 : 1;
+}
 
-// r2 of one pair.  PLAIN: the i coordinates already carry the lattice shift.
-template <int BOXKIND, bool PLAIN>
-__device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float xi,
-                                         float yi, float zi, const FastBox &fb) {
+// signed queue value of one pair (see code_variant)
+template <int BOXKIND, int VARIANT>
+__device__ __forceinline__ float pair_val(float xj, float yj, float zj, float xi,
+                                          float yi, float zi, const FastBox &fb) {
   const float dx = __fsub_rn(xj, xi), dy = __fsub_rn(yj, yi),
               dz = __fsub_rn(zj, zi);
-  if (PLAIN || BOXKIND == RDFK_BOX_NONE)
+  if (VARIANT == 0)
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-  return r2_fast<BOXKIND>(dx, dy, dz, fb);
+  if (VARIANT == 1)
+    return __fmaf_rn(-dz, dz, -__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return -r2_fast<BOXKIND>(dx, dy, dz, fb);
 }
 
 // Rare path: entry `s` of this lane's queue failed the band test.  Find the
@@ -916,7 +965,7 @@ template <int BOXKIND>
 __device__ __noinline__ int resolve_entry(
     int s, int lane, const unsigned char *mark, const int *glog, int nlog,
     const float *gi_cl, size_t np_i, const float *gj_f, size_t np_j,
-    float r2_cut, int swapped, const FrameParams *__restrict__ fp,
+    int swapped, const FrameParams *__restrict__ fp,
     const HistParams *__restrict__ hp) {
   int e = 0;
   for (int t = 1; t < nlog; ++t)
@@ -925,9 +974,10 @@ __device__ __noinline__ int resolve_entry(
   const int packed = glog[e];
   const int g = packed & 0xffffff, code = (packed >> 24) & 0x7f;
   const FastBox fb = load_fastbox(fp);
-  const bool plain = (BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN);
+  const int variant = code_variant<BOXKIND>(code);
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  if (BOXKIND == RDFK_BOX_ORTHO && plain) decode_shift(code, fb, sx, sy, sz);
+  if (variant == 1) decode_shift(code, fb, sx, sy, sz);
+  const float cut0 = fp->r2_cut[0], ncut1 = -fp->r2_cut[1];
   float xr[RI], yr[RI], zr[RI];
 #pragma unroll
   for (int r = 0; r < RI; ++r) {
@@ -940,14 +990,16 @@ __device__ __noinline__ int resolve_entry(
     const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
-      float r2;
-      if (plain)
-        r2 = pair_r2<BOXKIND, true>(xj, yj, zj, __fadd_rn(xr[r], sx),
-                                    __fadd_rn(yr[r], sy), __fadd_rn(zr[r], sz),
-                                    fb);
+      bool hit;
+      if (variant == 0)
+        hit = pair_val<BOXKIND, 0>(xj, yj, zj, xr[r], yr[r], zr[r], fb) < cut0;
+      else if (variant == 1)
+        hit = pair_val<BOXKIND, 1>(xj, yj, zj, __fadd_rn(xr[r], sx),
+                                   __fadd_rn(yr[r], sy), __fadd_rn(zr[r], sz),
+                                   fb) > ncut1;
       else
-        r2 = pair_r2<BOXKIND, false>(xj, yj, zj, xr[r], yr[r], zr[r], fb);
-      if (r2 < r2_cut) {
+        hit = pair_val<BOXKIND, 2>(xj, yj, zj, xr[r], yr[r], zr[r], fb) > ncut1;
+      if (hit) {
         if (rank == 0)
           return swapped
                      ? exact_bin<BOXKIND>(xj, yj, zj, xr[r], yr[r], zr[r], fp, hp)
@@ -961,17 +1013,17 @@ __device__ __noinline__ int resolve_entry(
 
 template <int BOXKIND>
 __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
-  static_assert(RI == 4 && GJ == 8, "hot loop is written for 4 x 8");
+  static_assert(RI == 4 && GJ == 8 && GPC == 16, "written for 4 x 8, 16 groups");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ HistParams s_hp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char *wbase = smem_raw + (size_t)warp * SM_WARP;
   float *q = reinterpret_cast<float *>(wbase);
   float *jst = reinterpret_cast<float *>(wbase + SM_Q);
-  int *glog = reinterpret_cast<int *>(wbase + SM_Q + SM_ST);
-  unsigned char *mark = wbase + SM_Q + SM_ST + SM_LOG;
-  unsigned int *hist_s =
-      reinterpret_cast<unsigned int *>(smem_raw + (size_t)NWARP * SM_WARP);
+  int *jcode = reinterpret_cast<int *>(wbase + SM_Q + SM_ST);
+  int *glog = reinterpret_cast<int *>(wbase + SM_Q + SM_ST + SM_CODE);
+  unsigned char *mark = wbase + SM_Q + SM_ST + SM_CODE + SM_LOG;
+  unsigned int *hist_s = reinterpret_cast<unsigned int *>(smem_raw + SM_FIXED);
 
   const int nbins = a.hp.nbins;
   const int copies = a.hist_copies;
@@ -979,6 +1031,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   const unsigned int sharers = copies ? (NWARP + copies - 1) / copies : 1;
   const uint32_t qbase = smem_u32(q + lane);
   uint32_t qaddr = qbase;
+  const unsigned int lt_mask = (1u << lane) - 1u;
 
   for (int b = tid; b < copies * nbins; b += TPB) hist_s[b] = 0u;
   if (tid == 0) s_hp = a.hp;
@@ -995,19 +1048,21 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     ++n_items;
     const int f = item / a.ncl_i, ic = item - f * a.ncl_i;
     const FrameParams *fp = a.fparams + f;
-    const float2 *tab = a.tables + (size_t)f * nbins;
+    const float2 *tab = a.tables + (size_t)f * 2 * (nbins + 1);
     const FastBox fb = load_fastbox(fp);
-    const float r2_cut = fp->r2_cut;
+    const float cut0 = fp->r2_cut[0], ncut1 = -fp->r2_cut[1];
     const int all_slow = fp->all_slow;
     const int shift_ok = fp->shift_ok;
     const size_t np_i = (size_t)a.np_i, np_j = (size_t)a.np_j;
     const float *gi_cl = a.gi + (size_t)f * 3 * np_i + (size_t)ic * CI;
     const float *gj_f = a.gj + (size_t)f * 3 * np_j;
+    const float *cbj = a.cbbj + (size_t)f * 6 * a.ncl_j;
+    const float *gbj = a.gbbj + (size_t)f * 6 * a.ngrp_j;
 
-    // cluster box (prune space)
+    // my cluster's box (prune space)
     float cc[3], ch[3];
     {
-      const float *cb = a.cbb + (size_t)f * 6 * a.ncl_i;
+      const float *cb = a.cbbi + (size_t)f * 6 * a.ncl_i;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         cc[k] = cb[(size_t)k * a.ncl_i + ic];
@@ -1018,28 +1073,48 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     const float wk[3] = {fp->wk[0], fp->wk[1], fp->wk[2]};
     const float rprune = fp->rprune, rshift = fp->rshift;
 
+    // lower bound of the distance between my cluster box and box (c, h);
+    // for ortho boxes also the lattice shift code of the pair
+    auto box_test = [&](const float *bb, int count, int at, int &code) -> bool {
+      float gap[3];
+      bool valid = true;
+      code = CODE_ZERO;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float cj = bb[(size_t)k * count + at];
+        const float hs = __fadd_rn(ch[k], bb[(size_t)(3 + k) * count + at]);
+        const float D = __fsub_rn(cj, cc[k]);
+        float d = fabsf(D);
+        d = fminf(d, __fsub_rn(per[k], d));
+        gap[k] = __fmul_rn(fmaxf(0.f, __fsub_rn(d, hs)), wk[k]);
+        if (BOXKIND == RDFK_BOX_ORTHO) {
+          // lattice shift of this (cluster, group) along k and whether it is
+          // the minimum image of every pair that can be in range
+          const float hp_ = __fmul_rn(0.5f, per[k]);
+          const int n = (D > hp_) ? 1 : ((D < -hp_) ? -1 : 0);
+          const float Dn = fabsf(__fsub_rn(D, __fmul_rn((float)n, per[k])));
+          if (per[k] < INFINITY) {
+            valid = valid && (__fadd_rn(__fadd_rn(Dn, hs), rshift) < per[k]);
+            code += n * (1 << (2 * k));
+          }
+        }
+      }
+      if (BOXKIND == RDFK_BOX_ORTHO && shift_ok && valid) code |= CODE_PLAIN;
+      else if (BOXKIND == RDFK_BOX_NONE) code = CODE_ZERO | CODE_PLAIN;
+      else code = CODE_ZERO;
+      if (BOXKIND == RDFK_BOX_TRI)
+        return fmaxf(gap[0], fmaxf(gap[1], gap[2])) <= rprune;
+      return __fmaf_rn(gap[2], gap[2],
+                       __fmaf_rn(gap[1], gap[1], __fmul_rn(gap[0], gap[0]))) <=
+             __fmul_rn(rprune, rprune);
+    };
+
     // i-atoms, shifted by the current group's lattice vector
     int cur_code = -1;
     float xs[RI], ys[RI], zs[RI];
-    auto set_shift = [&](int code) {
-      float sx = 0.f, sy = 0.f, sz = 0.f;
-      if (BOXKIND == RDFK_BOX_ORTHO && (code & CODE_PLAIN))
-        decode_shift(code, fb, sx, sy, sz);
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        xs[r] = __fadd_rn(gi_cl[r * 32 + lane], sx);
-        ys[r] = __fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
-        zs[r] = __fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
-      }
-      cur_code = code;
-    };
-
     int nlog = 0;
     unsigned int weight = 1u;
 
-    // bin everything queued so far (warp-uniform call sites only; the loop
-    // bound is warp-uniform and the per-lane work a structured `if`, see
-    // profiles/r1_notes.md section 4)
     auto maybe_flush = [&]() {
       if (wh && added > (1u << 30) / sharers) {
         for (int b = lane; b < nbins; b += 32) {
@@ -1049,45 +1124,73 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         added = 0;
       }
     };
+    auto count_bin = [&](int k) {
+      if (wh) atomicAdd(wh + k, weight);
+      else atomicAdd(a.hist + k, (unsigned long long)weight);
+    };
+
+    // bin everything queued so far.  Warp-uniform call sites only; four
+    // entries per lane in flight, no per-entry branches: the candidate bin
+    // comes from MUFU.SQRT and a magic-number round (no F2I), the tables have
+    // a "drop" entry in front, inactive slots are computed and discarded.
     auto drain = [&]() {
       __syncwarp();   // the group log was written by lane 0
-      const unsigned int n = (qaddr - qbase) >> 7;
-      const unsigned int nmax = __reduce_max_sync(0xffffffffu, n);
-      const float r2_low = fp->r2_low, inv_dr = fp->inv_dr, koff = fp->koff;
-      for (unsigned int s = 0; s < nmax; ++s) {
-        if (s < n) {
-          const float r2 = q[s * 32 + lane];
-          int k = __float2int_rd(__fmaf_rn(sqrt_approx(r2), inv_dr, koff));
-          k = max(0, min(k, nbins - 1));
-          const float2 t = __ldg(tab + k);
-          bool ok = r2 >= r2_low;
-          if (ok && !(r2 >= t.x && r2 < t.y)) {
-            k = resolve_entry<BOXKIND>((int)s, lane, mark, glog, nlog, gi_cl,
-                                       np_i, gj_f, np_j, r2_cut, a.swapped, fp,
-                                       &s_hp);
-            ++n_slow;
-            ok = k >= 0;
-          }
-          if (ok) {
-            if (wh) atomicAdd(wh + k, weight);
-            else atomicAdd(a.hist + k, (unsigned long long)weight);
+      const int n = (int)((qaddr - qbase) >> 7);
+      const int nmax = __reduce_max_sync(0xffffffffu, n);
+      const float inv_dr = fp->inv_dr, koffm = fp->koffm;
+      for (int s = 0; s < nmax; s += 4) {
+        float v[4];
+        int k[4];
+        bool act[4], inband[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = q[(s + u) * 32 + lane];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float r2 = fabsf(v[u]);
+          // floor(sqrt * inv_dr + koff) as round-to-nearest of (.. - 0.5),
+          // read out of the mantissa of (.. + 1.5 * 2^23)
+          const float kf = __fadd_rn(__fmaf_rn(sqrt_approx(r2), inv_dr, koffm), MAGIC);
+          k[u] = __float_as_int(kf) - 0x4B400000;
+          k[u] = max(-1, min(k[u], nbins - 1));
+          const float2 *tb = tab + ((__float_as_int(v[u]) < 0) ? nbins + 1 : 0);
+          const float2 t = __ldg(tb + k[u] + 1);
+          act[u] = s + u < n;
+          inband[u] = r2 >= t.x && r2 < t.y;
+        }
+        bool fail = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (act[u] && inband[u] && k[u] >= 0) count_bin(k[u]);
+          fail = fail || (act[u] && !inband[u]);
+        }
+        if (__any_sync(0xffffffffu, fail)) {
+#pragma unroll 1
+          for (int u = 0; u < 4; ++u) {
+            if (act[u] && !inband[u]) {
+              const int kk = resolve_entry<BOXKIND>(s + u, lane, mark, glog, nlog,
+                                                    gi_cl, np_i, gj_f, np_j,
+                                                    a.swapped, fp, &s_hp);
+              ++n_slow;
+              if (kk >= 0) count_bin(kk);
+            }
           }
         }
       }
       qaddr = qbase;
       nlog = 0;
       // shared counters are 32-bit: flush this warp's copy long before wrap
-      added += 64u * nmax;
+      added += 64u * (unsigned int)nmax;
       maybe_flush();
     };
 
-    // evaluate one staged j-group against my RI i-atoms
-    auto evaluate = [&](int packed, int slot) {
+    // evaluate staged j-group `slot` against my RI i-atoms
+    auto evaluate = [&](int slot) {
+      const int packed = jcode[slot];
       const int g = packed & 0xffffff, code = (packed >> 24) & 0x7f;
+      const float *js = jst + slot * 3 * GJ;
       ++n_groups;
       if (all_slow) {
         // frame not provably safe for fp32: every pair through the fp64 path
-        const float *js = jst + slot * 3 * GJ;
         for (int u = 0; u < GJ; ++u) {
           // padding is excluded by index here: the reference arithmetic maps
           // NaN to a distance in some box kinds
@@ -1102,10 +1205,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                               ? exact_bin<BOXKIND>(xj, yj, zj, xi, yi, zi, fp, &s_hp)
                               : exact_bin<BOXKIND>(xi, yi, zi, xj, yj, zj, fp, &s_hp);
             ++n_slow;
-            if (k >= 0) {
-              if (wh) atomicAdd(wh + k, weight);
-              else atomicAdd(a.hist + k, (unsigned long long)weight);
-            }
+            if (k >= 0) count_bin(k);
           }
         }
         added += 2u * PAIRS_PER_GROUP * 32u;
@@ -1120,8 +1220,18 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       if (lane == 0) glog[nlog] = packed;
       mark[nlog * 32 + lane] = (unsigned char)((qaddr - qbase) >> 7);
       ++nlog;
-      if (code != cur_code) set_shift(code);
-      const float *js = jst + slot * 3 * GJ;
+      const int variant = code_variant<BOXKIND>(code);
+      if (code != cur_code) {
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (variant == 1) decode_shift(code, fb, sx, sy, sz);
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          xs[r] = __fadd_rn(gi_cl[r * 32 + lane], sx);
+          ys[r] = __fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
+          zs[r] = __fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
+        }
+        cur_code = code;
+      }
       const float4 X0 = *reinterpret_cast<const float4 *>(js);
       const float4 X1 = *reinterpret_cast<const float4 *>(js + 4);
       const float4 Y0 = *reinterpret_cast<const float4 *>(js + GJ);
@@ -1131,128 +1241,113 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       const float xj8[GJ] = {X0.x, X0.y, X0.z, X0.w, X1.x, X1.y, X1.z, X1.w};
       const float yj8[GJ] = {Y0.x, Y0.y, Y0.z, Y0.w, Y1.x, Y1.y, Y1.z, Y1.w};
       const float zj8[GJ] = {Z0.x, Z0.y, Z0.z, Z0.w, Z1.x, Z1.y, Z1.z, Z1.w};
-      if ((BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN)) {
+      if (variant == 0) {
 #pragma unroll
         for (int u = 0; u < GJ; ++u)
 #pragma unroll
           for (int r = 0; r < RI; ++r)
             q_push(qaddr,
-                   pair_r2<BOXKIND, true>(xj8[u], yj8[u], zj8[u], xs[r], ys[r],
-                                          zs[r], fb),
-                   r2_cut);
-      } else {
+                   pair_val<BOXKIND, 0>(xj8[u], yj8[u], zj8[u], xs[r], ys[r],
+                                        zs[r], fb),
+                   cut0);
+      } else if (BOXKIND == RDFK_BOX_ORTHO && variant == 1) {
 #pragma unroll
         for (int u = 0; u < GJ; ++u)
 #pragma unroll
           for (int r = 0; r < RI; ++r)
-            q_push(qaddr,
-                   pair_r2<BOXKIND, false>(xj8[u], yj8[u], zj8[u], xs[r], ys[r],
-                                           zs[r], fb),
-                   r2_cut);
-      }
-    };
-
-    // cp.async pipeline: the copy of the newest group flies while the
-    // previous one is evaluated
-    int pend = -1, pend_slot = 0, next_slot = 0;
-    auto on_hit = [&](int packed) {
-      const int g = packed & 0xffffff;
-      __syncwarp();   // every lane is done reading the slot being refilled
-      if (lane < 6) {
-        const int plane = lane >> 1, half = lane & 1;
-        cp_async16(jst + next_slot * 3 * GJ + plane * GJ + half * 4,
-                   gj_f + (size_t)plane * np_j + (size_t)g * GJ + half * 4);
-      }
-      cp_async_commit();
-      if (pend >= 0) {
-        cp_async_wait<1>();
-        __syncwarp();
-        evaluate(pend, pend_slot);
-      }
-      pend = packed;
-      pend_slot = next_slot;
-      next_slot ^= 1;
-    };
-    auto finish = [&]() {
-      if (pend >= 0) {
-        cp_async_wait<0>();
-        __syncwarp();
-        evaluate(pend, pend_slot);
-        pend = -1;
-      }
-      if (!all_slow) drain();
-    };
-
-    // test `count` consecutive j-groups starting at gstart (index wraps)
-    auto scan_groups = [&](int gstart, int count) {
-      const float *gb = a.gbb + (size_t)f * 6 * a.ngrp_j;
-      for (int base = 0; base < count; base += 32) {
-        const int t = base + lane;
-        int g = gstart + t;
-        if (g >= a.ngrp_j) g -= a.ngrp_j;
-        bool pass = false;
-        int code = CODE_ZERO;
-        if (t < count) {
-          float gap[3];
-          bool valid = true;
+            q_push_neg(qaddr,
+                       pair_val<BOXKIND, 1>(xj8[u], yj8[u], zj8[u], xs[r],
+                                            ys[r], zs[r], fb),
+                       ncut1);
+      } else if (BOXKIND != RDFK_BOX_NONE) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float cj = gb[(size_t)k * a.ngrp_j + g];
-            const float hs = __fadd_rn(ch[k], gb[(size_t)(3 + k) * a.ngrp_j + g]);
-            const float D = __fsub_rn(cj, cc[k]);
-            float d = fabsf(D);
-            d = fminf(d, __fsub_rn(per[k], d));
-            gap[k] = __fmul_rn(fmaxf(0.f, __fsub_rn(d, hs)), wk[k]);
-            if (BOXKIND == RDFK_BOX_ORTHO) {
-              // lattice shift of this (cluster, group) along k and whether it
-              // is the minimum image of every pair that can be in range
-              const float hp_ = __fmul_rn(0.5f, per[k]);
-              const int n = (D > hp_) ? 1 : ((D < -hp_) ? -1 : 0);
-              const float Dn = fabsf(__fsub_rn(D, __fmul_rn((float)n, per[k])));
-              if (per[k] < INFINITY) {
-                valid = valid && (__fadd_rn(__fadd_rn(Dn, hs), rshift) < per[k]);
-                code += n * (1 << (2 * k));
-              }
-            }
-          }
-          if (BOXKIND == RDFK_BOX_TRI)
-            pass = fmaxf(gap[0], fmaxf(gap[1], gap[2])) <= rprune;
-          else
-            pass = __fmaf_rn(gap[2], gap[2],
-                             __fmaf_rn(gap[1], gap[1], __fmul_rn(gap[0], gap[0])))
-                   <= __fmul_rn(rprune, rprune);
-          if (BOXKIND == RDFK_BOX_NONE) code = CODE_ZERO | CODE_PLAIN;
-          else if (BOXKIND == RDFK_BOX_ORTHO && shift_ok && valid)
-            code |= CODE_PLAIN;
-          else code = CODE_ZERO;
-        }
-        unsigned int m = __ballot_sync(0xffffffffu, pass);
-        const int packed = g | (code << 24);
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          on_hit(__shfl_sync(0xffffffffu, packed, b));
-        }
+        for (int u = 0; u < GJ; ++u)
+#pragma unroll
+          for (int r = 0; r < RI; ++r)
+            q_push_neg(qaddr,
+                       pair_val<BOXKIND, 2>(xj8[u], yj8[u], zj8[u], xs[r],
+                                            ys[r], zs[r], fb),
+                       ncut1);
       }
-      finish();
     };
 
+    // Level 1: 32 j-clusters per round against my cluster box.  Level 2: the
+    // 16 group boxes of two surviving clusters per round.  Surviving groups
+    // are staged into shared memory by cp.async (each lane copies its own
+    // group) and evaluated one after the other.
+    int nrounds, cnt = 0;
     if (a.symmetric) {
-      // own cluster in full (weight 1: both orders and the self pairs are
-      // evaluated), then the circulant half of the other clusters (weight 2)
-      weight = 1u;
-      scan_groups(ic * GPC, GPC);
+      // round 0: my own cluster in full (weight 1: both orders and the self
+      // pairs are evaluated); then the circulant half of the others (weight 2)
       const int nt = a.ncl_i;
-      int cnt = (nt - 1) / 2;
+      cnt = (nt - 1) / 2;
       if ((nt & 1) == 0 && ic < nt / 2) ++cnt;
-      weight = 2u;
-      int gs = (ic + 1) * GPC;
-      if (gs >= a.ngrp_j) gs -= a.ngrp_j;
-      if (cnt > 0) scan_groups(gs, cnt * GPC);
+      nrounds = 1 + (cnt + 31) / 32;
     } else {
-      weight = 1u;
-      scan_groups(0, a.ngrp_j);
+      nrounds = (a.ncl_j + 31) / 32;
     }
+    for (int rr = 0; rr < nrounds; ++rr) {
+      int c = 0;
+      bool cv;
+      if (a.symmetric) {
+        if (rr == 0) {
+          c = ic;
+          cv = lane == 0;
+        } else {
+          if (rr == 1) {   // leaving my own cluster: the weight changes
+            if (!all_slow) drain();
+            weight = 2u;
+          }
+          const int t = (rr - 1) * 32 + lane;
+          cv = t < cnt;
+          c = ic + 1 + t;
+          if (c >= a.ncl_j) c -= a.ncl_j;
+          if (!cv) c = 0;
+        }
+      } else {
+        c = rr * 32 + lane;
+        cv = c < a.ncl_j;
+        if (!cv) c = 0;
+      }
+      int dummy;
+      unsigned int cmask =
+          __ballot_sync(0xffffffffu, cv && box_test(cbj, a.ncl_j, c, dummy));
+      while (cmask) {
+        int b0 = __ffs(cmask) - 1;
+        cmask &= cmask - 1;
+        int b1 = -1;
+        if (cmask) {
+          b1 = __ffs(cmask) - 1;
+          cmask &= cmask - 1;
+        }
+        const int c0 = __shfl_sync(0xffffffffu, c, b0);
+        const int c1 = __shfl_sync(0xffffffffu, c, b1 < 0 ? 0 : b1);
+        const bool gv = lane < GPC || b1 >= 0;
+        const int g = (lane < GPC ? c0 : c1) * GPC + (lane & (GPC - 1));
+        int code;
+        const bool gpass = gv && box_test(gbj, a.ngrp_j, g, code);
+        const unsigned int gmask = __ballot_sync(0xffffffffu, gpass);
+        if (!gmask) continue;
+        const int nh = __popc(gmask);
+        __syncwarp();   // every lane is done with the previous staging round
+        if (gpass) {
+          const int slot = __popc(gmask & lt_mask);
+          float *dst = jst + slot * 3 * GJ;
+          const float *src = gj_f + (size_t)g * GJ;
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            cp_async16(dst + pl * GJ, src + (size_t)pl * np_j);
+            cp_async16(dst + pl * GJ + 4, src + (size_t)pl * np_j + 4);
+          }
+          jcode[slot] = g | (code << 24);
+        }
+        cp_async_commit_wait_all();
+        __syncwarp();
+#pragma unroll 1
+        for (int h = 0; h < nh; ++h) evaluate(h);
+      }
+    }
+    if (!all_slow) drain();
   }
 
   __syncthreads();
@@ -1535,14 +1630,16 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   PairArgs a;
   a.gi = swap ? s2 : s1;
   a.gj = swap ? s1 : s2;
-  a.cbb = swap ? cbb2 : cbb1;
-  a.gbb = swap ? gbb1 : gbb2;
+  a.cbbi = swap ? cbb2 : cbb1;
+  a.cbbj = swap ? cbb1 : cbb2;
+  a.gbbj = swap ? gbb1 : gbb2;
   a.np_i = swap ? L.np2 : L.np1;
   a.np_j = swap ? L.np1 : L.np2;
   a.n_i = swap ? n2 : n1;
   a.n_j = swap ? n1 : n2;
   a.F = F;
   a.ncl_i = a.np_i / CI;
+  a.ncl_j = a.np_j / CI;
   a.ngrp_j = a.np_j / GJ;
   a.symmetric = same_group ? 1 : 0;
   a.swapped = swap ? 1 : 0;
@@ -1555,11 +1652,17 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   a.total_items = (int)total;
   a.fparams = fparams; a.tables = tables; a.hp = hp; a.hist = hist;
   a.header = header;
+  // warp-private histogram copies: all NWARP of them if two CTAs still fit on
+  // an SM, otherwise as many as one CTA can hold, otherwise global atomics
   const size_t per_copy = (size_t)hp.nbins * sizeof(unsigned int);
-  int copies = (int)(HIST_SMEM_BUDGET / per_copy);
+  const size_t two_cta = (size_t)(227 * 1024) / 2 - 1024 - SM_FIXED;
+  const size_t one_cta = (size_t)(227 * 1024) - 1024 - SM_FIXED;
+  int copies;
+  if ((size_t)NWARP * per_copy <= two_cta) copies = NWARP;
+  else copies = (int)(one_cta / per_copy);
   if (copies > NWARP) copies = NWARP;
   a.hist_copies = copies;
-  const size_t smem = (size_t)NWARP * SM_WARP + (size_t)copies * per_copy;
+  const size_t smem = (size_t)SM_FIXED + (size_t)copies * per_copy;
   CUDA_TRY(cudaFuncSetAttribute(pair_prune_kernel<BOXKIND>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));

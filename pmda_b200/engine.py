@@ -18,6 +18,7 @@ the host in frame order, like ``_reduce`` does in the reference.
 
 There is no CPU fallback: without the CUDA library / a GPU this raises.
 """
+import itertools
 import os
 import threading
 import time
@@ -139,6 +140,45 @@ def clear_cache():
             st.cache_used = 0
 
 
+# A cached frame block is identified by a token that is unique to the live
+# trajectory object (never ``id()``: ids are reused after garbage collection),
+# the frame range, and -- for in-memory trajectories, which the user may
+# modify in place -- a fingerprint of the block's coordinates.
+_token_counter = itertools.count(1)
+
+
+def _traj_token(traj):
+    tok = getattr(traj, "_pmda_b200_token", None)
+    if tok is None:
+        tok = next(_token_counter)
+        try:
+            traj._pmda_b200_token = tok
+            weakref.finalize(traj, _drop_token, tok)
+        except (AttributeError, TypeError):
+            return None          # cannot tag this reader: never cache it
+    return tok
+
+
+def _drop_token(tok):
+    with _states_lock:
+        for st in _states.values():
+            for key in [k for k in st.cache if k[0] == tok]:
+                _, _, nbytes = st.cache.pop(key)
+                st.cache_used -= nbytes
+
+
+def _fingerprint(pos, dims):
+    """cheap content check of an in-memory frame block (strided sample)"""
+    flat = pos.reshape(-1)
+    step = max(1, flat.size // 8192)
+    sample = np.ascontiguousarray(flat[::step]).view(np.uint32)
+    fp = int(np.bitwise_xor.reduce(sample)) ^ (int(sample.astype(np.uint64).sum()) << 1)
+    if dims is not None:
+        d = np.ascontiguousarray(dims, dtype=np.float32).view(np.uint32)
+        fp ^= int(d.astype(np.uint64).sum()) << 3
+    return fp
+
+
 _pinned_arrays = {}
 
 
@@ -258,7 +298,10 @@ class _Pipeline(object):
         self.pslot = 0
         self.h2d_done = [None, None]
         self.compute_done = [None, None]
-        self.traj_key = id(traj)
+        self.traj_key = _traj_token(traj)
+        #: in-memory trajectories hand out views: re-reading them is free, so
+        #: the cache entry is validated against the data on every hit
+        self.cheap_reads = getattr(traj, "frame_block", None) is not None
 
     def batches(self, frames):
         for lo in range(0, len(frames), self.batch_frames):
@@ -268,13 +311,23 @@ class _Pipeline(object):
         """-> (xyz_dev [B,N,3], dims_host, io_seconds, device slot or None)"""
         st = self.st
         t0 = time.time()
-        key = (self.traj_key, frames.start, frames.stop, frames.step)
-        hit = st.cache.get(key)
-        if hit is not None:
-            st.cache.move_to_end(key)
-            xyz_dev, dims, _ = hit
-            return xyz_dev, dims, time.time() - t0, None
-        pos, dims = _read_frames(self.traj, frames)
+        use_cache = self.traj_key is not None and Config.cache_bytes > 0
+        pos = dims = None
+        key = None
+        if use_cache:
+            fprint = 0
+            if self.cheap_reads:
+                pos, dims = _read_frames(self.traj, frames)
+                fprint = _fingerprint(pos, dims)
+            key = (self.traj_key, frames.start, frames.stop, frames.step,
+                   self.natoms, fprint)
+            hit = st.cache.get(key)
+            if hit is not None:
+                st.cache.move_to_end(key)
+                xyz_dev, dims_c, _ = hit
+                return xyz_dev, dims_c, time.time() - t0, None
+        if pos is None:
+            pos, dims = _read_frames(self.traj, frames)
         B = len(frames)
         if pos.shape[1:] != (self.natoms, 3):
             raise ValueError("trajectory frame has %r atoms, expected %d"
@@ -285,8 +338,14 @@ class _Pipeline(object):
             return xyz_dev, dims, time.time() - t0, None
         cap = self.batch_frames
         shape = (cap, self.natoms, 3)
-        cacheable = Config.cache_bytes > 0 and \
-            st.cache_used + nbytes <= Config.cache_bytes
+        cacheable = use_cache and nbytes <= Config.cache_bytes
+        if cacheable:
+            # same block with other contents (edited in-memory trajectory)
+            for k in [k for k in st.cache if k[:5] == key[:5]]:
+                st.cache_used -= st.cache.pop(k)[2]
+            while st.cache and st.cache_used + nbytes > Config.cache_bytes:
+                _, (_, _, freed) = st.cache.popitem(last=False)   # LRU
+                st.cache_used -= freed
         slot = None
         with torch.cuda.device(st.device):
             # destination: a cache entry of its own, or a rotating buffer
