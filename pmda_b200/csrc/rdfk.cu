@@ -93,10 +93,12 @@ struct FrameParams {
   float finv[3];  // fast path inverse, 0 when the axis has no PBC
   float tri[9];   // triclinic vectors, row-major (a; b; c)
   float tinv[3];  // fast path 1/ax, 1/by, 1/cz
-  // two decision tables per frame: [0] "tight" for pairs evaluated without any
-  // lattice shift (fp32 dx is the reference's own float difference), [1]
-  // "loose" for shifted / per-pair minimum-image arithmetic
-  float r2_cut[2];  // fp32 r2 >= r2_cut  => reference distance > r1 for sure
+  // error bounds of this frame's fp32 arithmetic against the reference, for
+  // the two decision tables of the call: [0] "tight" for pairs evaluated
+  // without any lattice shift (fp32 dx is the reference's own float
+  // difference), [1] "loose" for shifted / per-pair minimum-image arithmetic
+  float dlt[2];
+  float rbase;      // r1 * 1.001 + pruning slack (shift validity, see rshift)
   float inv_dr;     // nbins / (r1 - r0)
   float koffm;      // -r0 * inv_dr - 0.5 (then + 1.5 * 2^23: nearest = floor)
   int all_slow;   // fast path not provably safe for this frame
@@ -122,7 +124,8 @@ struct HistParams {
 struct WsHeader {
   unsigned long long stats[4];  // slow pairs, all-slow frames, items, pairs
   int work_counter;
-  int pad[7];
+  float r2_cut[2];  // fp32 r2 >= r2_cut[t] => reference distance > r1 for sure
+  int pad[5];
 };
 
 struct WsLayout {
@@ -152,7 +155,7 @@ static WsLayout ws_layout(int F, int n1, int n2, int nbins, int same_group) {
   w.fparams = off;
   off = align_up(off + sizeof(FrameParams) * (size_t)F, 256);
   w.tables = off;
-  off = align_up(off + sizeof(float2) * 2 * ((size_t)nbins + 1) * (size_t)F, 256);
+  off = align_up(off + sizeof(float2) * 2 * ((size_t)nbins + 1), 256);
   w.g1 = off;
   off = align_up(off + sizeof(float) * 3 * (size_t)w.np1 * (size_t)F, 256);
   w.g2 = same_group ? w.g1 : off;
@@ -426,18 +429,15 @@ __global__ __launch_bounds__(256) void stage_kernel(
   }
 }
 
-// One CTA per frame.  Builds FrameParams and the [lo_k, hi_k) table.
-// Band derivation: DESIGN.md section 3.
-__global__ void tables_kernel(int boxkind, const float *__restrict__ box,
+// One thread per frame: FrameParams.  Band derivation: DESIGN.md section 3.
+__global__ void params_kernel(int boxkind, const float *__restrict__ box,
                               const int *__restrict__ extents, HistParams hp,
-                              int debug_flags,
-                              FrameParams *__restrict__ fparams,
-                              float2 *__restrict__ tables) {
-  const int f = blockIdx.x;
-  __shared__ double s_delta[2];
-  __shared__ int s_slow;
+                              int debug_flags, int F,
+                              FrameParams *__restrict__ fparams) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
   FrameParams *fp = fparams + f;
-  if (threadIdx.x == 0) {
+  {
     const int *e = extents + f * 6;
     double X[3], A[3], lo3[3];
     bool slow = false, finite = true;
@@ -467,7 +467,7 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
     // coordinates and boxes, and the reference's own rounding (all ~1e-7
     // relative to the coordinate scale; 1e-5 leaves two orders of margin)
     double scale = 0.0;
-    bool shift_ok = (boxkind == RDFK_BOX_ORTHO);
+    bool shift_ok = (boxkind != RDFK_BOX_NONE);
     if (boxkind == RDFK_BOX_ORTHO) {
       for (int k = 0; k < 3; ++k) {
         const float L = b[k];
@@ -547,11 +547,24 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
       } else {
         finite = false;
       }
+      if (!finite) shift_ok = false;
     } else {
       for (int k = 0; k < 3; ++k) scale = fmax(scale, A[k] + X[k]);
     }
     const double slack = 2e-5 * scale;
     const double R = rmax * 1.001 + slack;
+    if (boxkind == RDFK_BOX_TRI && shift_ok) {
+      // shifted variant: the lattice vector n_a a + n_b b + n_c c is summed in
+      // fp32 (2 eps sum |column k|), added to the i atom (eps (A + R)), and
+      // the difference rounded (eps R); the reference rounds its float
+      // difference once (eps X).  Added to the brick bound (either variant
+      // may run in the frame).
+      const double col[3] = {fabs((double)b[0]) + fabs((double)b[3]) + fabs((double)b[6]),
+                             fabs((double)b[4]) + fabs((double)b[7]),
+                             fabs((double)b[8])};
+      for (int k = 0; k < 3; ++k)
+        dk[k] += EPS32 * (2.0 * col[k] + A[k] + 2.0 * R + X[k]) * 1.01;
+    }
     if (boxkind == RDFK_BOX_ORTHO) {
       for (int k = 0; k < 3; ++k) {
         if (!(fp->fl[k] > 0.f)) continue;
@@ -572,29 +585,55 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
     if (boxkind == RDFK_BOX_ORTHO)
       for (int k = 0; k < 3; ++k)
         if (fp->fl[k] > 0.f) dt[k] = EPS32 * R * 1.01;
-    s_delta[0] = (boxkind == RDFK_BOX_TRI)
-                     ? delta
-                     : sqrt(dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2]);
-    s_delta[1] = delta;
-    s_slow = slow ? 1 : 0;
+    // (triclinic, no shift: the reference's image (0,0,0) adds exact zeros to
+    // the same float difference -- identical components)
+    const double d0 = sqrt(dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2]);
+    fp->dlt[0] = slow ? 0.f : __double2float_ru(d0);
+    fp->dlt[1] = slow ? 0.f : __double2float_ru(delta);
     fp->all_slow = slow ? 1 : 0;
     const double inv_dr = (double)hp.nbins / (hp.r1 - hp.r0);
     fp->inv_dr = (float)inv_dr;
     fp->koffm = (float)(-hp.r0 * inv_dr - 0.5);
     fp->rprune = (float)((rmax + slack) * (1.0 + 1e-6));
-    fp->rshift = (float)((R + 8.0 * delta) * (1.0 + 1e-6));
-    if (shift_ok)
-      for (int k = 0; k < 3; ++k)
-        if (fp->fl[k] > 0.f && !((double)fp->rshift < 0.4999 * (double)fp->fl[k]))
-          shift_ok = false;
+    fp->rbase = __double2float_ru(R);
+    fp->rshift = INFINITY;   // set by tables_kernel
     fp->shift_ok = (shift_ok && !(debug_flags & 2)) ? 1 : 0;
     fp->prune_ok = (finite && slack < 1e15 && !(debug_flags & 1)) ? 1 : 0;
   }
+}
+
+// One CTA per call.  The two decision tables [lo_k, hi_k) are built for the
+// largest error bound of any frame of the call (a wider band is always
+// valid), so the pair kernel can keep them in shared memory.
+__global__ __launch_bounds__(256) void tables_kernel(
+    HistParams hp, int F, FrameParams *__restrict__ fparams,
+    float2 *__restrict__ tables, WsHeader *__restrict__ header) {
+  __shared__ float s_max[2][8];
+  float m0 = 0.f, m1 = 0.f;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    m0 = fmaxf(m0, fparams[f].dlt[0]);
+    m1 = fmaxf(m1, fparams[f].dlt[1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_max[0][threadIdx.x >> 5] = m0;
+    s_max[1][threadIdx.x >> 5] = m1;
+  }
   __syncthreads();
+  double dcall[2];
+  for (int w = 0; w < 2; ++w) {
+    float m = 0.f;
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, s_max[w][i]);
+    dcall[w] = (double)m;
+  }
   const double gam = 3.5 * EPS32;
   const int nbins = hp.nbins;
   for (int w = 0; w < 2; ++w) {
-    const double delta = s_delta[w];
+    const double delta = dcall[w];
     // T_hi(e): fp32 r2 >= T_hi  =>  reference d >= e (and > e)
     // T_lo(e): fp32 r2 <  T_lo  =>  reference d <  e
     auto t_hi = [&](double e) -> float {
@@ -611,7 +650,7 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
       return r > 0.f ? r : 0.f;
     };
     // entry k + 1 decides bin k; entry 0 is "certainly below r0: drop"
-    float2 *tab = tables + ((size_t)f * 2 + w) * (nbins + 1);
+    float2 *tab = tables + (size_t)w * (nbins + 1);
     for (int k = threadIdx.x; k <= nbins; k += blockDim.x) {
       float lo, hi;
       if (k == 0) {
@@ -622,11 +661,19 @@ __global__ void tables_kernel(int boxkind, const float *__restrict__ box,
         lo = (k == 1 && e0 <= 0.0) ? -INFINITY : t_hi(e0);
         hi = t_lo(e1);
       }
-      if (s_slow) { lo = INFINITY; hi = 0.f; }
       tab[k] = make_float2(lo, hi);
     }
-    if (threadIdx.x == 0)
-      fp->r2_cut[w] = s_slow ? INFINITY : t_hi(hp.edges[nbins]);
+    if (threadIdx.x == 0) header->r2_cut[w] = t_hi(hp.edges[nbins]);
+  }
+  // shift validity margin: must exceed sqrt(r2_cut) of the loose table
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    FrameParams *fp = fparams + f;
+    const double rs = ((double)fp->rbase + 8.0 * dcall[1]) * (1.0 + 1e-6);
+    fp->rshift = __double2float_ru(rs);
+    bool ok = fp->shift_ok != 0;
+    for (int k = 0; k < 3; ++k)
+      if (fp->fl[k] > 0.f && !(rs < 0.4999 * (double)fp->fl[k])) ok = false;
+    fp->shift_ok = ok ? 1 : 0;
   }
 }
 
@@ -888,7 +935,7 @@ constexpr int SM_MARK = LOGMAX * 32;           // queue marks (bytes)
 constexpr int SM_WARP = SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK;
 constexpr int SM_FIXED = NWARP * SM_WARP;
 
-// hit <=> r2 < cut.  NEG variants queue -r2 (hit <=> -r2 > -cut).
+// hit <=> r2 < cut
 __device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut) {
   asm volatile(
       "{\n"
@@ -901,20 +948,6 @@ __device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut) {
       : "f"(r2), "f"(cut)
       : "memory");
 }
-__device__ __forceinline__ void q_push_neg(uint32_t &qaddr, float r2n,
-                                           float ncut) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.gt.f32 p, %1, %2;\n"
-      "@p st.shared.f32 [%0], %1;\n"
-      "@p add.u32 %0, %0, 128;\n"
-      "}\n"
-      : "+r"(qaddr)
-      : "f"(r2n), "f"(ncut)
-      : "memory");
-}
-
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
                "l"(src)
@@ -924,48 +957,83 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// group code: bits 0-1 nx+1, 2-3 ny+1, 4-5 nz+1, bit 6 = one shift is valid
+// group code: bits 0-1 nx+1, 2-3 ny+1, 4-5 nz+1 (lattice shift of the group
+// pair), bit 6 = that one shift is the minimum image of every pair of the
+// group pair that can be in range
+template <int BOXKIND>
 __device__ __forceinline__ void decode_shift(int code, const FastBox &fb,
                                              float &sx, float &sy, float &sz) {
-  sx = __fmul_rn((float)((code & 3) - 1), fb.l0);
-  sy = __fmul_rn((float)(((code >> 2) & 3) - 1), fb.l1);
-  sz = __fmul_rn((float)(((code >> 4) & 3) - 1), fb.l2);
+  const float nx = (float)((code & 3) - 1), ny = (float)(((code >> 2) & 3) - 1),
+              nz = (float)(((code >> 4) & 3) - 1);
+  if (BOXKIND == RDFK_BOX_TRI) {
+    // n_a a + n_b b + n_c c, lower-triangular box
+    sx = __fadd_rn(__fadd_rn(__fmul_rn(nx, fb.ax), __fmul_rn(ny, fb.bx)),
+                   __fmul_rn(nz, fb.cx));
+    sy = __fadd_rn(__fmul_rn(ny, fb.by), __fmul_rn(nz, fb.cy));
+    sz = __fmul_rn(nz, fb.cz);
+  } else {
+    sx = __fmul_rn(nx, fb.l0);
+    sy = __fmul_rn(ny, fb.l1);
+    sz = __fmul_rn(nz, fb.l2);
+  }
 }
 constexpr int CODE_PLAIN = 64;
 constexpr int CODE_ZERO = 1 | (1 << 2) | (1 << 4);
-// which arithmetic a group code selects
-//   0: plain, no shift  -> +r2, tight table
-//   1: plain, shifted   -> -r2, loose table
-//   2: per-pair minimum image (ortho generic / triclinic brick) -> -r2, loose
-template <int BOXKIND>
-__device__ __forceinline__ int code_variant(int code) {
-  if (BOXKIND == RDFK_BOX_NONE) return 0;
-  if (BOXKIND == RDFK_BOX_TRI) return 2;
-  if (!(code & CODE_PLAIN)) return 2;
-  return (code & 63) == CODE_ZERO ? 0 : 1;
+// Decision-table class of a group: 0 = plain arithmetic without any shift
+// (fp32 dx is the reference's own float difference: tight table), 1 = shifted
+// or per-pair minimum image (loose table).  A work item is processed in two
+// passes, class 0 then class 1, so the table is warp-uniform in the drain.
+__device__ __forceinline__ int code_class(int code) {
+  return code == (CODE_ZERO | CODE_PLAIN) ? 0 : 1;
 }
 
-// signed queue value of one pair (see code_variant)
-template <int BOXKIND, int VARIANT>
-__device__ __forceinline__ float pair_val(float xj, float yj, float zj, float xi,
-                                          float yi, float zi, const FastBox &fb) {
-  const float dx = __fsub_rn(xj, xi), dy = __fsub_rn(yj, yi),
-              dz = __fsub_rn(zj, zi);
-  if (VARIANT == 0)
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: one issue slot, two lanes)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// r2 of one pair; (nxi, nyi, nzi) = minus the (shifted) i coordinates.
+// PLAIN: the lattice shift is already in the i coordinates.
+template <int BOXKIND, bool PLAIN>
+__device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float nxi,
+                                         float nyi, float nzi, const FastBox &fb) {
+  const float dx = __fadd_rn(xj, nxi), dy = __fadd_rn(yj, nyi),
+              dz = __fadd_rn(zj, nzi);
+  if (PLAIN || BOXKIND == RDFK_BOX_NONE)
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-  if (VARIANT == 1)
-    return __fmaf_rn(-dz, dz, -__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-  return -r2_fast<BOXKIND>(dx, dy, dz, fb);
+  return r2_fast<BOXKIND>(dx, dy, dz, fb);
 }
 
 // Rare path: entry `s` of this lane's queue failed the band test.  Find the
 // group it came from (marks), re-scan that group in the hot loop's order with
 // the hot loop's arithmetic, and bin the pair with the reference arithmetic.
+// Hot-loop order: j-atom pairs (0,1) (2,3) (4,5) (6,7); inside, i-atoms
+// 0..RI-1; inside, the even then the odd j-atom.
 template <int BOXKIND>
 __device__ __noinline__ int resolve_entry(
     int s, int lane, const unsigned char *mark, const int *glog, int nlog,
     const float *gi_cl, size_t np_i, const float *gj_f, size_t np_j,
-    int swapped, const FrameParams *__restrict__ fp,
+    int swapped, float cut, const FrameParams *__restrict__ fp,
     const HistParams *__restrict__ hp) {
   int e = 0;
   for (int t = 1; t < nlog; ++t)
@@ -974,10 +1042,9 @@ __device__ __noinline__ int resolve_entry(
   const int packed = glog[e];
   const int g = packed & 0xffffff, code = (packed >> 24) & 0x7f;
   const FastBox fb = load_fastbox(fp);
-  const int variant = code_variant<BOXKIND>(code);
+  const bool plain = (code & CODE_PLAIN) != 0;
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  if (variant == 1) decode_shift(code, fb, sx, sy, sz);
-  const float cut0 = fp->r2_cut[0], ncut1 = -fp->r2_cut[1];
+  if (plain && BOXKIND != RDFK_BOX_NONE) decode_shift<BOXKIND>(code, fb, sx, sy, sz);
   float xr[RI], yr[RI], zr[RI];
 #pragma unroll
   for (int r = 0; r < RI; ++r) {
@@ -986,32 +1053,30 @@ __device__ __noinline__ int resolve_entry(
     zr[r] = gi_cl[2 * np_i + r * 32 + lane];
   }
   const float *js = gj_f + (size_t)g * GJ;
-  for (int u = 0; u < GJ; ++u) {
-    const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
+  for (int up = 0; up < GJ / 2; ++up) {
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
-      bool hit;
-      if (variant == 0)
-        hit = pair_val<BOXKIND, 0>(xj, yj, zj, xr[r], yr[r], zr[r], fb) < cut0;
-      else if (variant == 1)
-        hit = pair_val<BOXKIND, 1>(xj, yj, zj, __fadd_rn(xr[r], sx),
-                                   __fadd_rn(yr[r], sy), __fadd_rn(zr[r], sz),
-                                   fb) > ncut1;
-      else
-        hit = pair_val<BOXKIND, 2>(xj, yj, zj, xr[r], yr[r], zr[r], fb) > ncut1;
-      if (hit) {
-        if (rank == 0)
-          return swapped
-                     ? exact_bin<BOXKIND>(xj, yj, zj, xr[r], yr[r], zr[r], fp, hp)
-                     : exact_bin<BOXKIND>(xr[r], yr[r], zr[r], xj, yj, zj, fp, hp);
-        --rank;
+      const float nxi = -__fadd_rn(xr[r], sx), nyi = -__fadd_rn(yr[r], sy),
+                  nzi = -__fadd_rn(zr[r], sz);
+      for (int h = 0; h < 2; ++h) {
+        const int u = 2 * up + h;
+        const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
+        const float r2 = plain ? pair_r2<BOXKIND, true>(xj, yj, zj, nxi, nyi, nzi, fb)
+                               : pair_r2<BOXKIND, false>(xj, yj, zj, nxi, nyi, nzi, fb);
+        if (r2 < cut) {
+          if (rank == 0)
+            return swapped
+                       ? exact_bin<BOXKIND>(xj, yj, zj, xr[r], yr[r], zr[r], fp, hp)
+                       : exact_bin<BOXKIND>(xr[r], yr[r], zr[r], xj, yj, zj, fp, hp);
+          --rank;
+        }
       }
     }
   }
   return -1;  // unreachable: the entry was produced by one of these pairs
 }
 
-template <int BOXKIND>
+template <int BOXKIND, bool GLOBAL_HIST>
 __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   static_assert(RI == 4 && GJ == 8 && GPC == 16, "written for 4 x 8, 16 groups");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1027,13 +1092,26 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
 
   const int nbins = a.hp.nbins;
   const int copies = a.hist_copies;
-  unsigned int *wh = copies ? hist_s + (size_t)(warp % copies) * nbins : nullptr;
-  const unsigned int sharers = copies ? (NWARP + copies - 1) / copies : 1;
+  // the two decision tables of the call: shared memory (after the histogram
+  // copies) unless the histogram itself did not fit
+  const int nb1 = nbins + 1;
+  const size_t hist_bytes = (((size_t)copies * nb1 * 4) + 15) & ~(size_t)15;
+  float2 *tab_s = reinterpret_cast<float2 *>(smem_raw + SM_FIXED + hist_bytes);
+  const uint32_t tab_s32 = smem_u32(tab_s);
+  const float cut0 = a.header->r2_cut[0], cut1 = a.header->r2_cut[1];
+  // every copy has a dummy slot in front (index -1: "drop")
+  const int hstride = nbins + 1;
+  unsigned int *wh =
+      GLOBAL_HIST ? nullptr : hist_s + (size_t)(warp % copies) * hstride + 1;
+  const uint32_t wh_s = GLOBAL_HIST ? 0u : smem_u32(wh);
+  const unsigned int sharers = GLOBAL_HIST ? 1 : (NWARP + copies - 1) / copies;
   const uint32_t qbase = smem_u32(q + lane);
   uint32_t qaddr = qbase;
   const unsigned int lt_mask = (1u << lane) - 1u;
 
-  for (int b = tid; b < copies * nbins; b += TPB) hist_s[b] = 0u;
+  for (int b = tid; b < copies * hstride; b += TPB) hist_s[b] = 0u;
+  if (!GLOBAL_HIST)
+    for (int b = tid; b < 2 * nb1; b += TPB) tab_s[b] = a.tables[b];
   if (tid == 0) s_hp = a.hp;
   __syncthreads();
 
@@ -1048,9 +1126,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     ++n_items;
     const int f = item / a.ncl_i, ic = item - f * a.ncl_i;
     const FrameParams *fp = a.fparams + f;
-    const float2 *tab = a.tables + (size_t)f * 2 * (nbins + 1);
     const FastBox fb = load_fastbox(fp);
-    const float cut0 = fp->r2_cut[0], ncut1 = -fp->r2_cut[1];
     const int all_slow = fp->all_slow;
     const int shift_ok = fp->shift_ok;
     const size_t np_i = (size_t)a.np_i, np_j = (size_t)a.np_j;
@@ -1073,8 +1149,8 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     const float wk[3] = {fp->wk[0], fp->wk[1], fp->wk[2]};
     const float rprune = fp->rprune, rshift = fp->rshift;
 
-    // lower bound of the distance between my cluster box and box (c, h);
-    // for ortho boxes also the lattice shift code of the pair
+    // lower bound of the distance between my cluster box and box (c, h), and
+    // the lattice shift code of the pair of boxes
     auto box_test = [&](const float *bb, int count, int at, int &code) -> bool {
       float gap[3];
       bool valid = true;
@@ -1087,20 +1163,23 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         float d = fabsf(D);
         d = fminf(d, __fsub_rn(per[k], d));
         gap[k] = __fmul_rn(fmaxf(0.f, __fsub_rn(d, hs)), wk[k]);
-        if (BOXKIND == RDFK_BOX_ORTHO) {
-          // lattice shift of this (cluster, group) along k and whether it is
-          // the minimum image of every pair that can be in range
+        if (BOXKIND != RDFK_BOX_NONE) {
+          // lattice shift of this pair of boxes along k, and whether it is
+          // the only image of any of their pairs that can be in range:
+          // every other image is at least (per - |D'| - hs) * wk away
           const float hp_ = __fmul_rn(0.5f, per[k]);
           const int n = (D > hp_) ? 1 : ((D < -hp_) ? -1 : 0);
           const float Dn = fabsf(__fsub_rn(D, __fmul_rn((float)n, per[k])));
           if (per[k] < INFINITY) {
-            valid = valid && (__fadd_rn(__fadd_rn(Dn, hs), rshift) < per[k]);
+            valid = valid &&
+                    (__fmaf_rn(__fadd_rn(Dn, hs), wk[k], rshift) <
+                     __fmul_rn(per[k], wk[k]));
             code += n * (1 << (2 * k));
           }
         }
       }
-      if (BOXKIND == RDFK_BOX_ORTHO && shift_ok && valid) code |= CODE_PLAIN;
-      else if (BOXKIND == RDFK_BOX_NONE) code = CODE_ZERO | CODE_PLAIN;
+      if (BOXKIND == RDFK_BOX_NONE) code = CODE_ZERO | CODE_PLAIN;
+      else if (shift_ok && valid) code |= CODE_PLAIN;
       else code = CODE_ZERO;
       if (BOXKIND == RDFK_BOX_TRI)
         return fmaxf(gap[0], fmaxf(gap[1], gap[2])) <= rprune;
@@ -1109,14 +1188,16 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
              __fmul_rn(rprune, rprune);
     };
 
-    // i-atoms, shifted by the current group's lattice vector
+    // minus my (shifted) i-atoms, each duplicated into a packed pair
     int cur_code = -1;
-    float xs[RI], ys[RI], zs[RI];
+    uint64_t nx2[RI], ny2[RI], nz2[RI];
     int nlog = 0;
     unsigned int weight = 1u;
+    int cls = 0;          // table class of the current pass
+    float cut = cut0;
 
     auto maybe_flush = [&]() {
-      if (wh && added > (1u << 30) / sharers) {
+      if (!GLOBAL_HIST && added > (1u << 30) / sharers) {
         for (int b = lane; b < nbins; b += 32) {
           const unsigned int v = atomicExch(wh + b, 0u);
           if (v) atomicAdd(a.hist + b, (unsigned long long)v);
@@ -1125,54 +1206,68 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       }
     };
     auto count_bin = [&](int k) {
-      if (wh) atomicAdd(wh + k, weight);
-      else atomicAdd(a.hist + k, (unsigned long long)weight);
+      if (GLOBAL_HIST) atomicAdd(a.hist + k, (unsigned long long)weight);
+      else atomicAdd(wh + k, weight);
     };
 
     // bin everything queued so far.  Warp-uniform call sites only; four
     // entries per lane in flight, no per-entry branches: the candidate bin
     // comes from MUFU.SQRT and a magic-number round (no F2I), the tables have
-    // a "drop" entry in front, inactive slots are computed and discarded.
+    // a "drop" entry in front, inactive slots go to a dummy histogram slot.
     auto drain = [&]() {
       __syncwarp();   // the group log was written by lane 0
       const int n = (int)((qaddr - qbase) >> 7);
       const int nmax = __reduce_max_sync(0xffffffffu, n);
       const float inv_dr = fp->inv_dr, koffm = fp->koffm;
+      const unsigned int toff = cls ? (unsigned int)nb1 + 1u : 1u;
       for (int s = 0; s < nmax; s += 4) {
         float v[4];
-        int k[4];
-        bool act[4], inband[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = q[(s + u) * 32 + lane];
+        unsigned int fail = 0u;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float r2 = fabsf(v[u]);
+          const float r2 = v[u];
           // floor(sqrt * inv_dr + koff) as round-to-nearest of (.. - 0.5),
           // read out of the mantissa of (.. + 1.5 * 2^23)
-          const float kf = __fadd_rn(__fmaf_rn(sqrt_approx(r2), inv_dr, koffm), MAGIC);
-          k[u] = __float_as_int(kf) - 0x4B400000;
-          k[u] = max(-1, min(k[u], nbins - 1));
-          const float2 *tb = tab + ((__float_as_int(v[u]) < 0) ? nbins + 1 : 0);
-          const float2 t = __ldg(tb + k[u] + 1);
-          act[u] = s + u < n;
-          inband[u] = r2 >= t.x && r2 < t.y;
+          const float kf =
+              __fadd_rn(__fmaf_rn(sqrt_approx(r2), inv_dr, koffm), MAGIC);
+          int k = __float_as_int(kf) - 0x4B400000;
+          k = max(-1, min(k, nbins - 1));
+          const unsigned int tidx = toff + (unsigned int)k;
+          float2 t;
+          if (GLOBAL_HIST) {
+            t = __ldg(a.tables + tidx);
+          } else {
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(t.x), "=f"(t.y)
+                         : "r"(tab_s32 + 8u * tidx));
+          }
+          const bool act = s + u < n;
+          const bool inband = r2 >= t.x && r2 < t.y;
+          if (GLOBAL_HIST) {
+            if (act && inband && k >= 0)
+              atomicAdd(a.hist + k, (unsigned long long)weight);
+          } else {
+            // unconditional: inactive / failed entries and k == -1
+            // ("certainly below r0") all land in the dummy slot in front
+            const int ke = (act && inband) ? k : -1;
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(
+                             wh_s + 4u * (unsigned int)ke),
+                         "r"(weight)
+                         : "memory");
+          }
+          if (act && !inband) fail |= 1u << u;
         }
-        bool fail = false;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (act[u] && inband[u] && k[u] >= 0) count_bin(k[u]);
-          fail = fail || (act[u] && !inband[u]);
-        }
-        if (__any_sync(0xffffffffu, fail)) {
-#pragma unroll 1
-          for (int u = 0; u < 4; ++u) {
-            if (act[u] && !inband[u]) {
-              const int kk = resolve_entry<BOXKIND>(s + u, lane, mark, glog, nlog,
-                                                    gi_cl, np_i, gj_f, np_j,
-                                                    a.swapped, fp, &s_hp);
-              ++n_slow;
-              if (kk >= 0) count_bin(kk);
-            }
+        if (__any_sync(0xffffffffu, fail != 0u)) {
+          while (fail) {
+            const int u = __ffs(fail) - 1;
+            fail &= fail - 1;
+            const int kk = resolve_entry<BOXKIND>(s + u, lane, mark, glog, nlog,
+                                                  gi_cl, np_i, gj_f, np_j,
+                                                  a.swapped, cut, fp, &s_hp);
+            ++n_slow;
+            if (kk >= 0) count_bin(kk);
           }
         }
       }
@@ -1220,61 +1315,69 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       if (lane == 0) glog[nlog] = packed;
       mark[nlog * 32 + lane] = (unsigned char)((qaddr - qbase) >> 7);
       ++nlog;
-      const int variant = code_variant<BOXKIND>(code);
       if (code != cur_code) {
         float sx = 0.f, sy = 0.f, sz = 0.f;
-        if (variant == 1) decode_shift(code, fb, sx, sy, sz);
+        if (BOXKIND != RDFK_BOX_NONE && (code & CODE_PLAIN))
+          decode_shift<BOXKIND>(code, fb, sx, sy, sz);
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-          xs[r] = __fadd_rn(gi_cl[r * 32 + lane], sx);
-          ys[r] = __fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
-          zs[r] = __fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
+          const float x = -__fadd_rn(gi_cl[r * 32 + lane], sx);
+          const float y = -__fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
+          const float z = -__fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
+          nx2[r] = pk2(x, x);
+          ny2[r] = pk2(y, y);
+          nz2[r] = pk2(z, z);
         }
         cur_code = code;
       }
-      const float4 X0 = *reinterpret_cast<const float4 *>(js);
-      const float4 X1 = *reinterpret_cast<const float4 *>(js + 4);
-      const float4 Y0 = *reinterpret_cast<const float4 *>(js + GJ);
-      const float4 Y1 = *reinterpret_cast<const float4 *>(js + GJ + 4);
-      const float4 Z0 = *reinterpret_cast<const float4 *>(js + 2 * GJ);
-      const float4 Z1 = *reinterpret_cast<const float4 *>(js + 2 * GJ + 4);
-      const float xj8[GJ] = {X0.x, X0.y, X0.z, X0.w, X1.x, X1.y, X1.z, X1.w};
-      const float yj8[GJ] = {Y0.x, Y0.y, Y0.z, Y0.w, Y1.x, Y1.y, Y1.z, Y1.w};
-      const float zj8[GJ] = {Z0.x, Z0.y, Z0.z, Z0.w, Z1.x, Z1.y, Z1.z, Z1.w};
-      if (variant == 0) {
+      if ((BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN)) {
+        // plain: 3 FADD2 + FMUL2 + 2 FFMA2 and 2 x 3 queue instructions per
+        // two pairs; j-atom pairs come straight out of the LDS.128 registers
 #pragma unroll
-        for (int u = 0; u < GJ; ++u)
+        for (int up = 0; up < GJ / 2; up += 2) {
+          const ulonglong2 X = *reinterpret_cast<const ulonglong2 *>(js + 2 * up);
+          const ulonglong2 Y = *reinterpret_cast<const ulonglong2 *>(js + GJ + 2 * up);
+          const ulonglong2 Z = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ + 2 * up);
 #pragma unroll
-          for (int r = 0; r < RI; ++r)
-            q_push(qaddr,
-                   pair_val<BOXKIND, 0>(xj8[u], yj8[u], zj8[u], xs[r], ys[r],
-                                        zs[r], fb),
-                   cut0);
-      } else if (BOXKIND == RDFK_BOX_ORTHO && variant == 1) {
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint64_t xj2 = h2 ? X.y : X.x, yj2 = h2 ? Y.y : Y.x,
+                           zj2 = h2 ? Z.y : Z.x;
 #pragma unroll
-        for (int u = 0; u < GJ; ++u)
+            for (int r = 0; r < RI; ++r) {
+              const uint64_t dx = add2(xj2, nx2[r]), dy = add2(yj2, ny2[r]),
+                             dz = add2(zj2, nz2[r]);
+              const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+              float ra, rb;
+              unpk2(t, ra, rb);
+              q_push(qaddr, ra, cut);
+              q_push(qaddr, rb, cut);
+            }
+          }
+        }
+      } else {
+        // per-pair minimum image (ortho rint / triclinic brick), same order
 #pragma unroll
-          for (int r = 0; r < RI; ++r)
-            q_push_neg(qaddr,
-                       pair_val<BOXKIND, 1>(xj8[u], yj8[u], zj8[u], xs[r],
-                                            ys[r], zs[r], fb),
-                       ncut1);
-      } else if (BOXKIND != RDFK_BOX_NONE) {
+        for (int up = 0; up < GJ / 2; ++up) {
+          const float2 X = *reinterpret_cast<const float2 *>(js + 2 * up);
+          const float2 Y = *reinterpret_cast<const float2 *>(js + GJ + 2 * up);
+          const float2 Z = *reinterpret_cast<const float2 *>(js + 2 * GJ + 2 * up);
 #pragma unroll
-        for (int u = 0; u < GJ; ++u)
-#pragma unroll
-          for (int r = 0; r < RI; ++r)
-            q_push_neg(qaddr,
-                       pair_val<BOXKIND, 2>(xj8[u], yj8[u], zj8[u], xs[r],
-                                            ys[r], zs[r], fb),
-                       ncut1);
+          for (int r = 0; r < RI; ++r) {
+            float nxi, nyi, nzi, dummy;
+            unpk2(nx2[r], nxi, dummy);
+            unpk2(ny2[r], nyi, dummy);
+            unpk2(nz2[r], nzi, dummy);
+            q_push(qaddr, pair_r2<BOXKIND, false>(X.x, Y.x, Z.x, nxi, nyi, nzi, fb), cut);
+            q_push(qaddr, pair_r2<BOXKIND, false>(X.y, Y.y, Z.y, nxi, nyi, nzi, fb), cut);
+          }
+        }
       }
     };
 
     // Level 1: 32 j-clusters per round against my cluster box.  Level 2: the
     // 16 group boxes of two surviving clusters per round.  Surviving groups
-    // are staged into shared memory by cp.async (each lane copies its own
-    // group) and evaluated one after the other.
+    // of the current table class are staged into shared memory by cp.async
+    // (each lane copies its own group) and evaluated one after the other.
     int nrounds, cnt = 0;
     if (a.symmetric) {
       // round 0: my own cluster in full (weight 1: both orders and the self
@@ -1286,75 +1389,85 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     } else {
       nrounds = (a.ncl_j + 31) / 32;
     }
-    for (int rr = 0; rr < nrounds; ++rr) {
-      int c = 0;
-      bool cv;
-      if (a.symmetric) {
-        if (rr == 0) {
-          c = ic;
-          cv = lane == 0;
-        } else {
-          if (rr == 1) {   // leaving my own cluster: the weight changes
-            if (!all_slow) drain();
-            weight = 2u;
+    // which table classes occur in this frame
+    int cls_lo = 0, cls_hi = 1;
+    if (all_slow) cls_lo = cls_hi = 1;             // class is ignored
+    else if (BOXKIND == RDFK_BOX_NONE) cls_hi = 0;
+    else if (!shift_ok) cls_lo = 1;
+    for (cls = cls_lo; cls <= cls_hi; ++cls) {
+      cut = cls ? cut1 : cut0;
+      weight = 1u;
+      for (int rr = 0; rr < nrounds; ++rr) {
+        int c = 0;
+        bool cv;
+        if (a.symmetric) {
+          if (rr == 0) {
+            c = ic;
+            cv = lane == 0;
+          } else {
+            if (rr == 1) {   // leaving my own cluster: the weight changes
+              if (!all_slow) drain();
+              weight = 2u;
+            }
+            const int t = (rr - 1) * 32 + lane;
+            cv = t < cnt;
+            c = ic + 1 + t;
+            if (c >= a.ncl_j) c -= a.ncl_j;
+            if (!cv) c = 0;
           }
-          const int t = (rr - 1) * 32 + lane;
-          cv = t < cnt;
-          c = ic + 1 + t;
-          if (c >= a.ncl_j) c -= a.ncl_j;
+        } else {
+          c = rr * 32 + lane;
+          cv = c < a.ncl_j;
           if (!cv) c = 0;
         }
-      } else {
-        c = rr * 32 + lane;
-        cv = c < a.ncl_j;
-        if (!cv) c = 0;
-      }
-      int dummy;
-      unsigned int cmask =
-          __ballot_sync(0xffffffffu, cv && box_test(cbj, a.ncl_j, c, dummy));
-      while (cmask) {
-        int b0 = __ffs(cmask) - 1;
-        cmask &= cmask - 1;
-        int b1 = -1;
-        if (cmask) {
-          b1 = __ffs(cmask) - 1;
+        int dummy;
+        unsigned int cmask =
+            __ballot_sync(0xffffffffu, cv && box_test(cbj, a.ncl_j, c, dummy));
+        while (cmask) {
+          int b0 = __ffs(cmask) - 1;
           cmask &= cmask - 1;
-        }
-        const int c0 = __shfl_sync(0xffffffffu, c, b0);
-        const int c1 = __shfl_sync(0xffffffffu, c, b1 < 0 ? 0 : b1);
-        const bool gv = lane < GPC || b1 >= 0;
-        const int g = (lane < GPC ? c0 : c1) * GPC + (lane & (GPC - 1));
-        int code;
-        const bool gpass = gv && box_test(gbj, a.ngrp_j, g, code);
-        const unsigned int gmask = __ballot_sync(0xffffffffu, gpass);
-        if (!gmask) continue;
-        const int nh = __popc(gmask);
-        __syncwarp();   // every lane is done with the previous staging round
-        if (gpass) {
-          const int slot = __popc(gmask & lt_mask);
-          float *dst = jst + slot * 3 * GJ;
-          const float *src = gj_f + (size_t)g * GJ;
-#pragma unroll
-          for (int pl = 0; pl < 3; ++pl) {
-            cp_async16(dst + pl * GJ, src + (size_t)pl * np_j);
-            cp_async16(dst + pl * GJ + 4, src + (size_t)pl * np_j + 4);
+          int b1 = -1;
+          if (cmask) {
+            b1 = __ffs(cmask) - 1;
+            cmask &= cmask - 1;
           }
-          jcode[slot] = g | (code << 24);
-        }
-        cp_async_commit_wait_all();
-        __syncwarp();
+          const int c0 = __shfl_sync(0xffffffffu, c, b0);
+          const int c1 = __shfl_sync(0xffffffffu, c, b1 < 0 ? 0 : b1);
+          const bool gv = lane < GPC || b1 >= 0;
+          const int g = (lane < GPC ? c0 : c1) * GPC + (lane & (GPC - 1));
+          int code = CODE_ZERO;
+          bool gpass = gv && box_test(gbj, a.ngrp_j, g, code);
+          if (!all_slow) gpass = gpass && code_class(code) == cls;
+          const unsigned int gmask = __ballot_sync(0xffffffffu, gpass);
+          if (!gmask) continue;
+          const int nh = __popc(gmask);
+          __syncwarp();   // every lane is done with the previous staging round
+          if (gpass) {
+            const int slot = __popc(gmask & lt_mask);
+            float *dst = jst + slot * 3 * GJ;
+            const float *src = gj_f + (size_t)g * GJ;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              cp_async16(dst + pl * GJ, src + (size_t)pl * np_j);
+              cp_async16(dst + pl * GJ + 4, src + (size_t)pl * np_j + 4);
+            }
+            jcode[slot] = g | (code << 24);
+          }
+          cp_async_commit_wait_all();
+          __syncwarp();
 #pragma unroll 1
-        for (int h = 0; h < nh; ++h) evaluate(h);
+          for (int h = 0; h < nh; ++h) evaluate(h);
+        }
       }
+      if (!all_slow) drain();
     }
-    if (!all_slow) drain();
   }
 
   __syncthreads();
-  if (copies) {
+  if (!GLOBAL_HIST) {
     for (int b = tid; b < nbins; b += TPB) {
       unsigned long long s = 0;
-      for (int c = 0; c < copies; ++c) s += hist_s[(size_t)c * nbins + b];
+      for (int c = 0; c < copies; ++c) s += hist_s[(size_t)c * hstride + 1 + b];
       if (s) atomicAdd(a.hist + b, s);
     }
   }
@@ -1603,7 +1716,7 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   uint32_t *cells = reinterpret_cast<uint32_t *>(ws + L.cells);
 
   init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(header, extents, F);
-  COUNT_LAUNCH(same_group ? 3 : 4);  // init + stage(s) + tables
+  COUNT_LAUNCH(same_group ? 4 : 5);  // init + stage(s) + params + tables
   stage_kernel<BOXKIND><<<dim3((L.np1 + 255) / 256, F), 256, 0, st>>>(
       xyz, natoms, idx1, n1, L.np1, box, g1, extents);
   if (!same_group)
@@ -1613,8 +1726,9 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   // shifted variant.  Results must not depend on either (tests/).
   int debug_flags = 0;
   if (const char *dbg = getenv("RDFK_DEBUG")) debug_flags = atoi(dbg);
-  tables_kernel<<<F, 256, 0, st>>>(BOXKIND, box, extents, hp, debug_flags,
-                                   fparams, tables);
+  params_kernel<<<(F + 127) / 128, 128, 0, st>>>(BOXKIND, box, extents, hp,
+                                                 debug_flags, F, fparams);
+  tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header);
 
   int rc = sort_side<BOXKIND>(g1, n1, L.np1, L.bits1, F, fparams, keys, lrank,
                               cells, s1, gbb1, cbb1, st);
@@ -1654,27 +1768,30 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   a.header = header;
   // warp-private histogram copies: all NWARP of them if two CTAs still fit on
   // an SM, otherwise as many as one CTA can hold, otherwise global atomics
-  const size_t per_copy = (size_t)hp.nbins * sizeof(unsigned int);
+  const size_t per_copy = ((size_t)hp.nbins + 1) * sizeof(unsigned int);
+  const size_t tab_bytes = 2 * ((size_t)hp.nbins + 1) * sizeof(float2) + 16;
   const size_t two_cta = (size_t)(227 * 1024) / 2 - 1024 - SM_FIXED;
   const size_t one_cta = (size_t)(227 * 1024) - 1024 - SM_FIXED;
-  int copies;
-  if ((size_t)NWARP * per_copy <= two_cta) copies = NWARP;
-  else copies = (int)(one_cta / per_copy);
+  int copies = 0;
+  if ((size_t)NWARP * per_copy + tab_bytes <= two_cta) copies = NWARP;
+  else if (per_copy + tab_bytes <= one_cta)
+    copies = (int)((one_cta - tab_bytes) / per_copy);
   if (copies > NWARP) copies = NWARP;
   a.hist_copies = copies;
-  const size_t smem = (size_t)SM_FIXED + (size_t)copies * per_copy;
-  CUDA_TRY(cudaFuncSetAttribute(pair_prune_kernel<BOXKIND>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem =
+      (size_t)SM_FIXED + (copies ? (size_t)copies * per_copy + tab_bytes : 0);
+  void (*kern)(const PairArgs) = copies ? pair_prune_kernel<BOXKIND, false>
+                                        : pair_prune_kernel<BOXKIND, true>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, pair_prune_kernel<BOXKIND>, TPB, smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem));
   if (occ < 1) return set_err(RDFK_ECUDA, "pair_prune_kernel does not fit%s%s");
   long long grid = (long long)sms * occ;
   const long long need = (total + NWARP - 1) / NWARP;
   if (grid > need) grid = need;
   if (grid > 0) {
-    pair_prune_kernel<BOXKIND><<<(int)grid, TPB, smem, st>>>(a);
+    kern<<<(int)grid, TPB, smem, st>>>(a);
     COUNT_LAUNCH(1);
   }
 
