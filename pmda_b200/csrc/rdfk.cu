@@ -130,7 +130,7 @@ struct WsHeader {
 
 struct WsLayout {
   size_t header, extents, fparams, tables, g1, g2, s1, s2, gbb1, gbb2, cbb1,
-      cbb2, keys, lrank, cells, total;
+      cbb2, qbb1, qbb2, keys, lrank, cells, total;
   int np1, np2, bits1, bits2;
 };
 
@@ -177,6 +177,11 @@ static WsLayout ws_layout(int F, int n1, int n2, int nbins, int same_group) {
   w.cbb2 = same_group ? w.cbb1 : off;
   if (!same_group)
     off = align_up(off + sizeof(float) * 6 * (size_t)(w.np2 / CI) * (size_t)F, 256);
+  w.qbb1 = off;
+  off = align_up(off + sizeof(float) * 6 * (size_t)(w.np1 / 32) * (size_t)F, 256);
+  w.qbb2 = same_group ? w.qbb1 : off;
+  if (!same_group)
+    off = align_up(off + sizeof(float) * 6 * (size_t)(w.np2 / 32) * (size_t)F, 256);
   // counting-sort scratch, shared by the two groups (used one after the other)
   const int npmax = w.np1 > w.np2 ? w.np1 : w.np2;
   w.bits1 = grid_bits(n1);
@@ -826,15 +831,15 @@ __global__ __launch_bounds__(256) void scatter_kernel(
   }
 }
 
-// Boxes in prune space: one thread per 8-atom group; 16 neighbouring threads
-// combine into the 128-atom cluster box.  Layout [F][6][count]:
+// Boxes in prune space: one thread per 8-atom group; 4 neighbouring threads
+// combine into a 32-atom quarter box, 16 into the 128-atom cluster box.  Layout [F][6][count]:
 // centre x|y|z, half-width x|y|z.  Empty box: half-width -inf (never
 // reached); frame without pruning: half-width +inf (always reached).
 template <int BOXKIND>
 __global__ __launch_bounds__(256) void bbox_kernel(
     const float *__restrict__ sorted, int np,
     const FrameParams *__restrict__ fparams, float *__restrict__ gbb,
-    float *__restrict__ cbb) {
+    float *__restrict__ qbb, float *__restrict__ cbb) {
   const int f = blockIdx.y;
   const int ngrp = np / GJ, ncl = np / CI;   // ngrp is a multiple of GPC
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -877,13 +882,16 @@ __global__ __launch_bounds__(256) void bbox_kernel(
     }
   };
   if (live) emit(gbb, ngrp, g, lo, hi);
+  // 4 groups -> one 32-atom quarter (the atoms one register index of the pair
+  // kernel holds), 4 quarters -> the cluster
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {
+  for (int o = 1; o < GPC; o <<= 1) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
       hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
     }
+    if (o == 2 && live && (g & 3) == 0) emit(qbb, ngrp / 4, g / 4, lo, hi);
   }
   if (live && (g & (GPC - 1)) == 0) emit(cbb, ncl, g / GPC, lo, hi);
 }
@@ -892,6 +900,7 @@ struct PairArgs {
   const float *gi;    // sorted [F][3][np_i]: the side whose clusters are work items
   const float *gj;    // sorted [F][3][np_j]
   const float *cbbi;  // cluster boxes of the i side [F][6][ncl_i]
+  const float *qbbi;  // quarter boxes of the i side [F][6][4 * ncl_i]
   const float *cbbj;  // cluster boxes of the j side [F][6][ncl_j]
   const float *gbbj;  // group boxes of the j side   [F][6][ngrp_j]
   int np_i, np_j, F;
@@ -925,14 +934,18 @@ constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
 constexpr int NSTAGE = 32;    // staged j-groups per warp (one test round)
 constexpr int PAIRS_PER_GROUP = GJ * RI;   // per lane
 static_assert(QS >= 2 * PAIRS_PER_GROUP, "queue must absorb one group");
-static_assert(QS < 256 && QS % 4 == 0, "marks are bytes; drain is 4-wide");
+constexpr int DW = 8;         // queue entries per lane in flight in the drain
+static_assert(QS <= 64 && QS % DW == 0, "fail mask is 64 bits; drain is DW-wide");
 
 constexpr int SM_Q = QS * 32 * 4;              // bytes per warp: queue
 constexpr int SM_ST = NSTAGE * 3 * GJ * 4;     // staged j-groups
-constexpr int SM_CODE = NSTAGE * 4;            // their (group, code) words
-constexpr int SM_LOG = LOGMAX * 4;             // group log
+constexpr int SM_CODE = NSTAGE * 4;            // their (group, code, quarter mask)
+constexpr int SM_LOG = LOGMAX * 4;             // group log (same words)
 constexpr int SM_MARK = LOGMAX * 32;           // queue marks (bytes)
-constexpr int SM_WARP = SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK;
+constexpr int SM_DUMMY = 32 * 4;               // per-lane sink for dead atomics
+constexpr int SM_QB = 24 * 4;                  // my 4 quarter boxes [6][4]
+constexpr int SM_WARP =
+    SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK + SM_DUMMY + SM_QB;
 constexpr int SM_FIXED = NWARP * SM_WARP;
 
 // hit <=> r2 < cut
@@ -979,6 +992,12 @@ __device__ __forceinline__ void decode_shift(int code, const FastBox &fb,
 }
 constexpr int CODE_PLAIN = 64;
 constexpr int CODE_ZERO = 1 | (1 << 2) | (1 << 4);
+// staged / logged group word: group index (20 bits) | quarter mask (4 bits:
+// which 32-atom quarters of my cluster can reach the group) | code (7 bits)
+constexpr int G_BITS = 20;
+__device__ __forceinline__ int pack_group(int g, int qmask, int code) {
+  return g | (qmask << G_BITS) | (code << 24);
+}
 // Decision-table class of a group: 0 = plain arithmetic without any shift
 // (fp32 dx is the reference's own float difference: tight table), 1 = shifted
 // or per-pair minimum image (loose table).  A work item is processed in two
@@ -1027,8 +1046,8 @@ __device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float nxi
 // Rare path: entry `s` of this lane's queue failed the band test.  Find the
 // group it came from (marks), re-scan that group in the hot loop's order with
 // the hot loop's arithmetic, and bin the pair with the reference arithmetic.
-// Hot-loop order: j-atom pairs (0,1) (2,3) (4,5) (6,7); inside, i-atoms
-// 0..RI-1; inside, the even then the odd j-atom.
+// Hot-loop order: the quarters of the mask (i-atom r = 0..RI-1), inside the
+// eight j-atoms in order.
 template <int BOXKIND>
 __device__ __noinline__ int resolve_entry(
     int s, int lane, const unsigned char *mark, const int *glog, int nlog,
@@ -1040,36 +1059,28 @@ __device__ __noinline__ int resolve_entry(
     if ((int)mark[t * 32 + lane] <= s) e = t;
   int rank = s - (int)mark[e * 32 + lane];
   const int packed = glog[e];
-  const int g = packed & 0xffffff, code = (packed >> 24) & 0x7f;
+  const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
+            code = (packed >> 24) & 0x7f;
   const FastBox fb = load_fastbox(fp);
   const bool plain = (code & CODE_PLAIN) != 0;
   float sx = 0.f, sy = 0.f, sz = 0.f;
   if (plain && BOXKIND != RDFK_BOX_NONE) decode_shift<BOXKIND>(code, fb, sx, sy, sz);
-  float xr[RI], yr[RI], zr[RI];
-#pragma unroll
-  for (int r = 0; r < RI; ++r) {
-    xr[r] = gi_cl[r * 32 + lane];
-    yr[r] = gi_cl[np_i + r * 32 + lane];
-    zr[r] = gi_cl[2 * np_i + r * 32 + lane];
-  }
   const float *js = gj_f + (size_t)g * GJ;
-  for (int up = 0; up < GJ / 2; ++up) {
-#pragma unroll
-    for (int r = 0; r < RI; ++r) {
-      const float nxi = -__fadd_rn(xr[r], sx), nyi = -__fadd_rn(yr[r], sy),
-                  nzi = -__fadd_rn(zr[r], sz);
-      for (int h = 0; h < 2; ++h) {
-        const int u = 2 * up + h;
-        const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
-        const float r2 = plain ? pair_r2<BOXKIND, true>(xj, yj, zj, nxi, nyi, nzi, fb)
-                               : pair_r2<BOXKIND, false>(xj, yj, zj, nxi, nyi, nzi, fb);
-        if (r2 < cut) {
-          if (rank == 0)
-            return swapped
-                       ? exact_bin<BOXKIND>(xj, yj, zj, xr[r], yr[r], zr[r], fp, hp)
-                       : exact_bin<BOXKIND>(xr[r], yr[r], zr[r], xj, yj, zj, fp, hp);
-          --rank;
-        }
+  for (int r = 0; r < RI; ++r) {
+    if (!((qmask >> r) & 1)) continue;
+    const float xr = gi_cl[r * 32 + lane], yr = gi_cl[np_i + r * 32 + lane],
+                zr = gi_cl[2 * np_i + r * 32 + lane];
+    const float nxi = -__fadd_rn(xr, sx), nyi = -__fadd_rn(yr, sy),
+                nzi = -__fadd_rn(zr, sz);
+    for (int u = 0; u < GJ; ++u) {
+      const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
+      const float r2 = plain ? pair_r2<BOXKIND, true>(xj, yj, zj, nxi, nyi, nzi, fb)
+                             : pair_r2<BOXKIND, false>(xj, yj, zj, nxi, nyi, nzi, fb);
+      if (r2 < cut) {
+        if (rank == 0)
+          return swapped ? exact_bin<BOXKIND>(xj, yj, zj, xr, yr, zr, fp, hp)
+                         : exact_bin<BOXKIND>(xr, yr, zr, xj, yj, zj, fp, hp);
+        --rank;
       }
     }
   }
@@ -1088,6 +1099,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   int *jcode = reinterpret_cast<int *>(wbase + SM_Q + SM_ST);
   int *glog = reinterpret_cast<int *>(wbase + SM_Q + SM_ST + SM_CODE);
   unsigned char *mark = wbase + SM_Q + SM_ST + SM_CODE + SM_LOG;
+  const uint32_t dummy_s =
+      smem_u32(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK) + 4u * lane;
+  float *qb = reinterpret_cast<float *>(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG +
+                                        SM_MARK + SM_DUMMY);   // [6][4]
   unsigned int *hist_s = reinterpret_cast<unsigned int *>(smem_raw + SM_FIXED);
 
   const int nbins = a.hp.nbins;
@@ -1149,8 +1164,16 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     const float wk[3] = {fp->wk[0], fp->wk[1], fp->wk[2]};
     const float rprune = fp->rprune, rshift = fp->rshift;
 
-    // lower bound of the distance between my cluster box and box (c, h), and
-    // the lattice shift code of the pair of boxes
+    // my four quarter boxes -> shared memory [6][4]
+    __syncwarp();
+    if (lane < 24) {
+      const int k = lane >> 2, r = lane & 3;
+      qb[lane] = a.qbbi[((size_t)f * 6 + k) * (4 * (size_t)a.ncl_i) + 4 * ic + r];
+    }
+    __syncwarp();
+
+    // lower bound of the distance between my cluster box and box (c, h) of
+    // the j side, and the lattice shift code of the pair of boxes
     auto box_test = [&](const float *bb, int count, int at, int &code) -> bool {
       float gap[3];
       bool valid = true;
@@ -1187,10 +1210,41 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                        __fmaf_rn(gap[1], gap[1], __fmul_rn(gap[0], gap[0]))) <=
              __fmul_rn(rprune, rprune);
     };
+    // which of my quarters can reach group box `at`
+    auto quarter_mask = [&](const float *bb, int count, int at) -> int {
+      float cj[3], hj[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        cj[k] = bb[(size_t)k * count + at];
+        hj[k] = bb[(size_t)(3 + k) * count + at];
+      }
+      int m = 0;
+#pragma unroll
+      for (int r = 0; r < RI; ++r) {
+        float gap[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float d = fabsf(__fsub_rn(cj[k], qb[k * 4 + r]));
+          d = fminf(d, __fsub_rn(per[k], d));
+          gap[k] = __fmul_rn(
+              fmaxf(0.f, __fsub_rn(d, __fadd_rn(hj[k], qb[(3 + k) * 4 + r]))),
+              wk[k]);
+        }
+        bool ok;
+        if (BOXKIND == RDFK_BOX_TRI)
+          ok = fmaxf(gap[0], fmaxf(gap[1], gap[2])) <= rprune;
+        else
+          ok = __fmaf_rn(gap[2], gap[2],
+                         __fmaf_rn(gap[1], gap[1], __fmul_rn(gap[0], gap[0]))) <=
+               __fmul_rn(rprune, rprune);
+        m |= ok ? (1 << r) : 0;
+      }
+      return m;
+    };
 
-    // minus my (shifted) i-atoms, each duplicated into a packed pair
+    // minus my (shifted) i-atoms
     int cur_code = -1;
-    uint64_t nx2[RI], ny2[RI], nz2[RI];
+    float nxs[RI], nys[RI], nzs[RI];
     int nlog = 0;
     unsigned int weight = 1u;
     int cls = 0;          // table class of the current pass
@@ -1220,13 +1274,15 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       const int nmax = __reduce_max_sync(0xffffffffu, n);
       const float inv_dr = fp->inv_dr, koffm = fp->koffm;
       const unsigned int toff = cls ? (unsigned int)nb1 + 1u : 1u;
-      for (int s = 0; s < nmax; s += 4) {
-        float v[4];
+      unsigned long long failmask = 0ull;   // bit s: entry s needs the fp64 path
+      for (int s = 0; s < nmax; s += DW) {
+        float v[DW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = q[(s + u) * 32 + lane];
+        for (int u = 0; u < DW; ++u) v[u] = q[(s + u) * 32 + lane];
         unsigned int fail = 0u;
+        const int rem = n - s;   // entries s .. s + rem - 1 are live
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DW; ++u) {
           const float r2 = v[u];
           // floor(sqrt * inv_dr + koff) as round-to-nearest of (.. - 0.5),
           // read out of the mantissa of (.. + 1.5 * 2^23)
@@ -1243,33 +1299,39 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                          : "=f"(t.x), "=f"(t.y)
                          : "r"(tab_s32 + 8u * tidx));
           }
-          const bool act = s + u < n;
+          const bool act = rem > u;
           const bool inband = r2 >= t.x && r2 < t.y;
           if (GLOBAL_HIST) {
             if (act && inband && k >= 0)
               atomicAdd(a.hist + k, (unsigned long long)weight);
           } else {
-            // unconditional: inactive / failed entries and k == -1
-            // ("certainly below r0") all land in the dummy slot in front
-            const int ke = (act && inband) ? k : -1;
-            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(
-                             wh_s + 4u * (unsigned int)ke),
-                         "r"(weight)
+            // unconditional: inactive / failed entries go to this lane's own
+            // dummy word (same-address atomics of one warp serialise), k == -1
+            // ("certainly below r0") to the dummy slot in front of the copy
+            const uint32_t ha = (act && inband) ? wh_s + 4u * (unsigned int)k
+                                                : dummy_s;
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ha), "r"(weight)
                          : "memory");
           }
           if (act && !inband) fail |= 1u << u;
         }
-        if (__any_sync(0xffffffffu, fail != 0u)) {
-          while (fail) {
-            const int u = __ffs(fail) - 1;
-            fail &= fail - 1;
-            const int kk = resolve_entry<BOXKIND>(s + u, lane, mark, glog, nlog,
-                                                  gi_cl, np_i, gj_f, np_j,
-                                                  a.swapped, cut, fp, &s_hp);
-            ++n_slow;
-            if (kk >= 0) count_bin(kk);
-          }
+        failmask |= (unsigned long long)fail << s;
+      }
+      // the rare band failures, after the pipelined loop
+      if (__any_sync(0xffffffffu, failmask != 0ull)) {
+        while (failmask) {
+          const int se = __ffsll((long long)failmask) - 1;
+          failmask &= failmask - 1;
+          const int kk = resolve_entry<BOXKIND>(se, lane, mark, glog, nlog, gi_cl,
+                                                np_i, gj_f, np_j, a.swapped, cut,
+                                                fp, &s_hp);
+          ++n_slow;
+          if (kk >= 0) count_bin(kk);
         }
+        // lanes leave the loop at different times and are not guaranteed to
+        // reconverge by themselves; the log and marks they read are reused
+        // as soon as drain() returns
+        __syncwarp();
       }
       qaddr = qbase;
       nlog = 0;
@@ -1281,9 +1343,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     // evaluate staged j-group `slot` against my RI i-atoms
     auto evaluate = [&](int slot) {
       const int packed = jcode[slot];
-      const int g = packed & 0xffffff, code = (packed >> 24) & 0x7f;
+      const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
+                code = (packed >> 24) & 0x7f;
       const float *js = jst + slot * 3 * GJ;
-      ++n_groups;
+      n_groups += __popc(qmask);
       if (all_slow) {
         // frame not provably safe for fp32: every pair through the fp64 path
         for (int u = 0; u < GJ; ++u) {
@@ -1293,7 +1356,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
           const float xj = js[u], yj = js[GJ + u], zj = js[2 * GJ + u];
 #pragma unroll 1
           for (int r = 0; r < RI; ++r) {
-            if (ic * CI + r * 32 + lane >= a.n_i) continue;
+            if (!((qmask >> r) & 1) || ic * CI + r * 32 + lane >= a.n_i) continue;
             const float xi = gi_cl[r * 32 + lane], yi = gi_cl[np_i + r * 32 + lane],
                         zi = gi_cl[2 * np_i + r * 32 + lane];
             const int k = a.swapped
@@ -1321,31 +1384,32 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
           decode_shift<BOXKIND>(code, fb, sx, sy, sz);
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-          const float x = -__fadd_rn(gi_cl[r * 32 + lane], sx);
-          const float y = -__fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
-          const float z = -__fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
-          nx2[r] = pk2(x, x);
-          ny2[r] = pk2(y, y);
-          nz2[r] = pk2(z, z);
+          nxs[r] = -__fadd_rn(gi_cl[r * 32 + lane], sx);
+          nys[r] = -__fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
+          nzs[r] = -__fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
         }
         cur_code = code;
       }
       if ((BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN)) {
         // plain: 3 FADD2 + FMUL2 + 2 FFMA2 and 2 x 3 queue instructions per
-        // two pairs; j-atom pairs come straight out of the LDS.128 registers
+        // two pairs; j-atom pairs come straight out of the LDS.128 registers,
+        // the i-atom is a broadcast scalar operand.  Quarters that cannot
+        // reach the group are skipped (warp-uniform).
 #pragma unroll
-        for (int up = 0; up < GJ / 2; up += 2) {
-          const ulonglong2 X = *reinterpret_cast<const ulonglong2 *>(js + 2 * up);
-          const ulonglong2 Y = *reinterpret_cast<const ulonglong2 *>(js + GJ + 2 * up);
-          const ulonglong2 Z = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ + 2 * up);
+        for (int r = 0; r < RI; ++r) {
+          if (!((qmask >> r) & 1)) continue;
+          const uint64_t nx2 = pk2(nxs[r], nxs[r]), ny2 = pk2(nys[r], nys[r]),
+                         nz2 = pk2(nzs[r], nzs[r]);
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const uint64_t xj2 = h2 ? X.y : X.x, yj2 = h2 ? Y.y : Y.x,
-                           zj2 = h2 ? Z.y : Z.x;
+          for (int up = 0; up < GJ / 2; up += 2) {
+            const ulonglong2 X = *reinterpret_cast<const ulonglong2 *>(js + 2 * up);
+            const ulonglong2 Y = *reinterpret_cast<const ulonglong2 *>(js + GJ + 2 * up);
+            const ulonglong2 Z = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ + 2 * up);
 #pragma unroll
-            for (int r = 0; r < RI; ++r) {
-              const uint64_t dx = add2(xj2, nx2[r]), dy = add2(yj2, ny2[r]),
-                             dz = add2(zj2, nz2[r]);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const uint64_t dx = add2(h2 ? X.y : X.x, nx2),
+                             dy = add2(h2 ? Y.y : Y.x, ny2),
+                             dz = add2(h2 ? Z.y : Z.x, nz2);
               const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
               float ra, rb;
               unpk2(t, ra, rb);
@@ -1357,18 +1421,17 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       } else {
         // per-pair minimum image (ortho rint / triclinic brick), same order
 #pragma unroll
-        for (int up = 0; up < GJ / 2; ++up) {
-          const float2 X = *reinterpret_cast<const float2 *>(js + 2 * up);
-          const float2 Y = *reinterpret_cast<const float2 *>(js + GJ + 2 * up);
-          const float2 Z = *reinterpret_cast<const float2 *>(js + 2 * GJ + 2 * up);
+        for (int r = 0; r < RI; ++r) {
+          if (!((qmask >> r) & 1)) continue;
 #pragma unroll
-          for (int r = 0; r < RI; ++r) {
-            float nxi, nyi, nzi, dummy;
-            unpk2(nx2[r], nxi, dummy);
-            unpk2(ny2[r], nyi, dummy);
-            unpk2(nz2[r], nzi, dummy);
-            q_push(qaddr, pair_r2<BOXKIND, false>(X.x, Y.x, Z.x, nxi, nyi, nzi, fb), cut);
-            q_push(qaddr, pair_r2<BOXKIND, false>(X.y, Y.y, Z.y, nxi, nyi, nzi, fb), cut);
+          for (int u4 = 0; u4 < GJ; u4 += 4) {
+            const float4 X = *reinterpret_cast<const float4 *>(js + u4);
+            const float4 Y = *reinterpret_cast<const float4 *>(js + GJ + u4);
+            const float4 Z = *reinterpret_cast<const float4 *>(js + 2 * GJ + u4);
+            q_push(qaddr, pair_r2<BOXKIND, false>(X.x, Y.x, Z.x, nxs[r], nys[r], nzs[r], fb), cut);
+            q_push(qaddr, pair_r2<BOXKIND, false>(X.y, Y.y, Z.y, nxs[r], nys[r], nzs[r], fb), cut);
+            q_push(qaddr, pair_r2<BOXKIND, false>(X.z, Y.z, Z.z, nxs[r], nys[r], nzs[r], fb), cut);
+            q_push(qaddr, pair_r2<BOXKIND, false>(X.w, Y.w, Z.w, nxs[r], nys[r], nzs[r], fb), cut);
           }
         }
       }
@@ -1435,9 +1498,13 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
           const int c1 = __shfl_sync(0xffffffffu, c, b1 < 0 ? 0 : b1);
           const bool gv = lane < GPC || b1 >= 0;
           const int g = (lane < GPC ? c0 : c1) * GPC + (lane & (GPC - 1));
-          int code = CODE_ZERO;
+          int code = CODE_ZERO, qmask = 0;
           bool gpass = gv && box_test(gbj, a.ngrp_j, g, code);
           if (!all_slow) gpass = gpass && code_class(code) == cls;
+          if (gpass) {
+            qmask = quarter_mask(gbj, a.ngrp_j, g);
+            gpass = qmask != 0;
+          }
           const unsigned int gmask = __ballot_sync(0xffffffffu, gpass);
           if (!gmask) continue;
           const int nh = __popc(gmask);
@@ -1451,7 +1518,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
               cp_async16(dst + pl * GJ, src + (size_t)pl * np_j);
               cp_async16(dst + pl * GJ + 4, src + (size_t)pl * np_j + 4);
             }
-            jcode[slot] = g | (code << 24);
+            jcode[slot] = pack_group(g, qmask, code);
           }
           cp_async_commit_wait_all();
           __syncwarp();
@@ -1480,7 +1547,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     if (n_items) atomicAdd(&a.header->stats[2], (unsigned long long)n_items);
     if (n_groups)
       atomicAdd(&a.header->stats[3],
-                (unsigned long long)n_groups * (unsigned long long)(CI * GJ));
+                (unsigned long long)n_groups * (unsigned long long)(32 * GJ));
   }
 }
 
@@ -1678,7 +1745,7 @@ template <int BOXKIND>
 static int sort_side(const float *staged, int n, int np, int bits, int F,
                      const FrameParams *fparams, uint32_t *keys,
                      uint32_t *lrank, uint32_t *cells, float *sorted,
-                     float *gbb, float *cbb, cudaStream_t st) {
+                     float *gbb, float *qbb, float *cbb, cudaStream_t st) {
   const size_t ncell = (size_t)1 << (3 * bits);
   CUDA_TRY(cudaMemsetAsync(cells, 0, sizeof(uint32_t) * ncell * (size_t)F, st));
   key_kernel<BOXKIND><<<dim3((n + 255) / 256, F), 256, 0, st>>>(
@@ -1688,7 +1755,7 @@ static int sort_side(const float *staged, int n, int np, int bits, int F,
                                                         keys, lrank, cells,
                                                         sorted);
   bbox_kernel<BOXKIND><<<dim3((np / GJ + 255) / 256, F), 256, 0, st>>>(
-      sorted, np, fparams, gbb, cbb);
+      sorted, np, fparams, gbb, qbb, cbb);
   COUNT_LAUNCH(4);
   return RDFK_OK;
 }
@@ -1730,12 +1797,14 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
                                                  debug_flags, F, fparams);
   tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header);
 
+  float *qbb1 = reinterpret_cast<float *>(ws + L.qbb1);
+  float *qbb2 = reinterpret_cast<float *>(ws + L.qbb2);
   int rc = sort_side<BOXKIND>(g1, n1, L.np1, L.bits1, F, fparams, keys, lrank,
-                              cells, s1, gbb1, cbb1, st);
+                              cells, s1, gbb1, qbb1, cbb1, st);
   if (rc) return rc;
   if (!same_group) {
     rc = sort_side<BOXKIND>(g2, n2, L.np2, L.bits2, F, fparams, keys, lrank,
-                            cells, s2, gbb2, cbb2, st);
+                            cells, s2, gbb2, qbb2, cbb2, st);
     if (rc) return rc;
   }
 
@@ -1745,6 +1814,7 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   a.gi = swap ? s2 : s1;
   a.gj = swap ? s1 : s2;
   a.cbbi = swap ? cbb2 : cbb1;
+  a.qbbi = swap ? qbb2 : qbb1;
   a.cbbj = swap ? cbb1 : cbb2;
   a.gbbj = swap ? gbb1 : gbb2;
   a.np_i = swap ? L.np2 : L.np1;
@@ -1757,8 +1827,8 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   a.ngrp_j = a.np_j / GJ;
   a.symmetric = same_group ? 1 : 0;
   a.swapped = swap ? 1 : 0;
-  if (a.ngrp_j >= (1 << 24))
-    return set_err(RDFK_EINVAL, "group too large (max 134e6 atoms)%s%s");
+  if (a.ngrp_j >= (1 << G_BITS))
+    return set_err(RDFK_EINVAL, "group too large (max 8.3e6 atoms)%s%s");
   const long long total = (long long)a.ncl_i * F;
   if (total > 0x7fff0000LL)
     return set_err(RDFK_EINVAL, "too many cluster work items in one call; "
