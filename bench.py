@@ -293,9 +293,10 @@ def run_b200(args):
         return 0
 
     # ---- roofline of the dominant kernel (rank 0) --------------------------
-    # rdfk_rdf_hist = init + stage + tables + pair_tile; the CUDA events of
-    # engine._Timer bracket the whole call on the compute stream, and the tile
-    # kernel is > 99 % of it (profiles/): its launch duration is kernel_s/calls
+    # rdfk_rdf_hist = init + stage + params + tables + sort (4) + pair_prune;
+    # the CUDA events of engine._Timer bracket the whole call on the compute
+    # stream, and the pair kernel is ~97 % of it (profiles/): its launch
+    # duration is taken as kernel_s / calls
     peak = _cabi.measure_fp32_peak()
     # timing.compute holds every frame's kernel time (each frame ran on one
     # rank), so kernel_s sums over ranks and work/kernel_s is the per-GPU rate
@@ -314,21 +315,38 @@ def run_b200(args):
     hbm_src = "MEASURED_PEAKS.json" if hbm_peak else "fallback 6650 GB/s"
     hbm_peak = hbm_peak or 6650.0
     alg_bytes = 12.0 * n1 * frames_all            # g1 == g2: read once
+    # what the pair kernel actually evaluated in its last launch (one batch of
+    # fps frames): the sort + box tests skip group pairs that provably hold no
+    # pair in range, so evaluated << algorithmic
+    frames_last = max(1, stats["tile_items"] // (-(-n1 // 128)))
+    eval_pairs_per_frame = stats["tile_pairs"] / float(frames_last)
+    eval_frac = eval_pairs_per_frame / (float(n1) * n2)
+    eval_rate = eval_pairs_per_frame * frames_all / kernel_s
     roofline = {
-        "bound": "fp32", "kernel": "pair_tile_kernel<ORTHO>",
+        "bound": "fp32", "kernel": "pair_prune_kernel<ORTHO>",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": None,
         "peak_source": "FFMA loop measured live (rdfk_measure_fp32_peak); "
                        "MEASURED_PEAKS.json has no FP32 figure",
         "flop_per_pair": FLOP_PER_PAIR,
         "launch_ms": 1e3 * kernel_s / args.steps / world,
-        "evaluated_pairs_last_launch": stats["tile_pairs"],
+        "evaluated": {
+            "pairs_last_launch": stats["tile_pairs"],
+            "fraction_of_pair_matrix": eval_frac,
+            "pairs_per_s": eval_rate,
+            "tflops_at_8_flop_per_evaluated_pair": eval_rate * 8.0 / 1e12,
+            "frac_of_peak": eval_rate * 8.0 / 1e12 / peak,
+        },
         "fp64_rechecked_pairs_last_launch": stats["slow_pairs"],
         "hbm": {"algorithmic_GBps": alg_bytes / kernel_s / 1e9,
                 "peak_GBps": hbm_peak, "peak_source": hbm_src,
                 "frac": alg_bytes / kernel_s / 1e9 / hbm_peak},
-        "note": "algorithmic flops = 20 x N1 x N2 per frame (full matrix); "
-                "the symmetric schedule evaluates about half of it",
+        "note": "achieved = ALGORITHMIC flops (20 x N1 x N2 per frame, "
+                "SURVEY 8d) / kernel time: exact pruning evaluates only "
+                "`evaluated.fraction_of_pair_matrix` of the pair matrix "
+                "(3 sub + 3 mul + 2 add = 8 flop per evaluated pair), so frac "
+                "exceeds 1; the kernel is issue/latency bound, not FMA bound "
+                "(profiles/r1_notes.md)",
     }
 
     cpu = None

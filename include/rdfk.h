@@ -112,9 +112,9 @@ int rdfk_rdf_sites(const float *xyz, int F, int natoms, const int *idxA,
 
 /* counters of the last rdfk_rdf_hist call that used `workspace`:
  * out_host[0] = pairs sent to the fp64 re-check, out_host[1] = frames that
- * ran entirely on the fp64 path, out_host[2] = tile work items executed,
- * out_host[3] = pairs evaluated by the fp32 tile kernel.
- * Synchronises `stream`.                                                    */
+ * ran entirely on the fp64 path, out_host[2] = (frame, 128-atom cluster) work
+ * items executed, out_host[3] = pairs evaluated by the pair kernel (after the
+ * bounding-box pruning).  Synchronises `stream`.                             */
 int rdfk_rdf_stats(const void *workspace, unsigned long long *out_host,
                    void *stream);
 

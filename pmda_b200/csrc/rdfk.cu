@@ -679,6 +679,7 @@ __global__ __launch_bounds__(256) void tables_kernel(
     for (int k = 0; k < 3; ++k)
       if (fp->fl[k] > 0.f && !(rs < 0.4999 * (double)fp->fl[k])) ok = false;
     fp->shift_ok = ok ? 1 : 0;
+    if (fp->all_slow) atomicAdd(&header->stats[1], 1ull);
   }
 }
 

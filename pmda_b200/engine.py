@@ -304,8 +304,15 @@ class _Pipeline(object):
         self.cheap_reads = getattr(traj, "frame_block", None) is not None
 
     def batches(self, frames):
-        for lo in range(0, len(frames), self.batch_frames):
-            yield frames[lo:lo + self.batch_frames]
+        """equal-sized batches of at most ``batch_frames`` frames (a short
+        last batch would leave the persistent kernel's tail under-filled)"""
+        n = len(frames)
+        if n == 0:
+            return
+        nb = -(-n // self.batch_frames)
+        size = -(-n // nb)
+        for lo in range(0, n, size):
+            yield frames[lo:lo + size]
 
     def fetch(self, frames):
         """-> (xyz_dev [B,N,3], dims_host, io_seconds, device slot or None)"""
