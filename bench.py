@@ -319,17 +319,34 @@ def run_b200(args):
     # fps frames): the sort + box tests skip group pairs that provably hold no
     # pair in range, so evaluated << algorithmic
     frames_last = max(1, stats["tile_items"] // (-(-n1 // 128)))
+    frames_per_launch = frames_last
+    # DRAM traffic of the pair kernel per launch, from the committed ncu
+    # capture (bytes per frame x frames of one launch); null when the workload
+    # is not the one the capture was taken on
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as fh:
+            tr = json.load(fh)
+        if args.n_atoms == N_ATOMS:
+            traffic = tr["dram_bytes_per_frame"] * frames_per_launch
+    except Exception:
+        pass
     eval_pairs_per_frame = stats["tile_pairs"] / float(frames_last)
     eval_frac = eval_pairs_per_frame / (float(n1) * n2)
     eval_rate = eval_pairs_per_frame * frames_all / kernel_s
     roofline = {
         "bound": "fp32", "kernel": "pair_prune_kernel<ORTHO>",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": "profiles/r1b_traffic.json: dram__bytes_read+write of "
+                          "one ncu --set full capture, per frame x frames per "
+                          "launch",
         "peak_source": "FFMA loop measured live (rdfk_measure_fp32_peak); "
                        "MEASURED_PEAKS.json has no FP32 figure",
         "flop_per_pair": FLOP_PER_PAIR,
-        "launch_ms": 1e3 * kernel_s / args.steps / world,
+        "launch_ms": 1e3 * kernel_s / args.steps / world /
+                     max(1.0, fps / float(frames_per_launch)),
+        "frames_per_launch": frames_per_launch,
         "evaluated": {
             "pairs_last_launch": stats["tile_pairs"],
             "fraction_of_pair_matrix": eval_frac,
