@@ -90,7 +90,7 @@ class ClockSampler(object):
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index),
                  "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()

@@ -41,6 +41,9 @@ class Config(object):
     cache_bytes = int(os.environ.get("PMDA_B200_CACHE_BYTES", 48 << 30))
     #: page-lock in-memory trajectories so H2D runs straight from them
     pin_host = os.environ.get("PMDA_B200_PIN_HOST", "1") != "0"
+    #: host threads copying frame blocks into the pinned ring
+    copy_threads = int(os.environ.get("PMDA_B200_COPY_THREADS",
+                                      min(8, os.cpu_count() or 1)))
 
 
 # --------------------------------------------------------------------------
@@ -192,6 +195,11 @@ def _maybe_pin(arr):
     key = base.__array_interface__["data"][0]
     if key in _pinned_arrays or base.nbytes < (1 << 20):
         return
+    if not base.flags.writeable:
+        # read-only file mappings (NpyTrajectory) cannot be page-locked in
+        # place; their blocks go through the pinned staging ring
+        _pinned_arrays[key] = False
+        return
     try:
         rc = torch.cuda.cudart().cudaHostRegister(key, base.nbytes, 0)
         ok = int(rc) == 0
@@ -213,6 +221,29 @@ def _unpin(key):
 # --------------------------------------------------------------------------
 # trajectory access
 # --------------------------------------------------------------------------
+_copy_pool = None
+
+
+def _copy_frames(dst, src):
+    """``dst[...] = src`` frame-parallel: for a file-backed trajectory this
+    copy *is* the file read (page cache -> pinned ring), and numpy releases
+    the GIL while it runs, so a few threads multiply the ingest bandwidth."""
+    global _copy_pool
+    n = len(src)
+    nthreads = min(Config.copy_threads, n)
+    if nthreads <= 1 or src.nbytes < (8 << 20):
+        np.copyto(dst, src)
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _copy_pool = ThreadPoolExecutor(max_workers=Config.copy_threads)
+    cuts = np.linspace(0, n, nthreads + 1).astype(int)
+    futs = [_copy_pool.submit(np.copyto, dst[a:b], src[a:b])
+            for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    for fu in futs:
+        fu.result()
+
+
 def _read_frames(traj, frames):
     """-> (positions float32 [B,N,3], dimensions float32 [B,6] | None)"""
     fb = getattr(traj, "frame_block", None)
@@ -341,7 +372,10 @@ class _Pipeline(object):
                              % (pos.shape[1:], self.natoms))
         nbytes = B * self.frame_bytes
         if not st.is_cuda:
-            xyz_dev = torch.from_numpy(np.ascontiguousarray(pos))
+            host = np.ascontiguousarray(pos)
+            if not host.flags.writeable:        # read-only file mapping
+                host = np.array(host)
+            xyz_dev = torch.from_numpy(host)
             return xyz_dev, dims, time.time() - t0, None
         cap = self.batch_frames
         shape = (cap, self.natoms, 3)
@@ -372,7 +406,7 @@ class _Pipeline(object):
             # source: the trajectory array itself when it is page-locked,
             # otherwise a rotating pinned staging buffer
             src = None
-            if pos.flags.c_contiguous:
+            if pos.flags.c_contiguous and pos.flags.writeable:
                 _maybe_pin(pos)
                 cand = torch.from_numpy(pos)
                 if cand.is_pinned():
@@ -385,7 +419,7 @@ class _Pipeline(object):
                                                 pin_memory=True)
                 if self.h2d_done[ps] is not None:
                     self.h2d_done[ps].synchronize()
-                np.copyto(st.pinned[ps][:B].numpy(), pos)
+                _copy_frames(st.pinned[ps][:B].numpy(), pos)
                 src = st.pinned[ps][:B]
             else:
                 ps = None
