@@ -1371,10 +1371,11 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         maybe_flush();
         return;
       }
-      // room for one more group in every lane's queue and in the log?
+      // room for this group (8 pairs per active quarter) in every lane's
+      // queue, and for one more entry in the log?
       if (nlog == LOGMAX ||
           __any_sync(0xffffffffu,
-                     qaddr > qbase + (QS - PAIRS_PER_GROUP) * 128))
+                     qaddr > qbase + (QS - GJ * __popc(qmask)) * 128))
         drain();
       if (lane == 0) glog[nlog] = packed;
       mark[nlog * 32 + lane] = (unsigned char)((qaddr - qbase) >> 7);

@@ -134,3 +134,59 @@ def test_triclinic_right_angles_given_as_vectors():
     d_o = c_oracle.distance_array(a, a, [L, L, L, 90, 90, 90])
     d_t = c_oracle.distance_array(a, a, [L, L, L, 90, 90, 89.9999])
     assert np.max(np.abs(d_o - d_t)) < 1e-3
+
+
+def _hist_agrees_up_to_edge_ties(count, dist64, edges, tol):
+    """`count` (oracle, float32-flavoured arithmetic) against the histogram of
+    independently computed float64 distances: they may differ only by pairs
+    that sit within `tol` of a bin edge."""
+    ind = np.histogram(dist64, bins=edges)[0]
+    near = np.array([np.sum(np.abs(dist64 - e) < tol) for e in edges])
+    slack = near[:-1] + near[1:]
+    assert np.all(np.abs(count - ind) <= slack), (count - ind, slack)
+    assert abs(int(count.sum()) - int(ind.sum())) <= near[0] + near[-1]
+
+
+def test_ortho_histogram_against_scipy_periodic_kdtree():
+    """independent implementation: scipy's periodic cKDTree (float64,
+    true minimum image) must give the oracle's histogram up to edge ties"""
+    from scipy.spatial import cKDTree
+    gen = np.random.default_rng(12)
+    L = np.array([28.0, 31.0, 26.0])
+    a = (gen.random((700, 3)) * L).astype(np.float32)
+    b = (gen.random((900, 3)) * L).astype(np.float32)
+    hi = np.nextafter(L.astype(np.float32), np.float32(0))
+    a, b = np.minimum(a, hi), np.minimum(b, hi)
+    nbins, rng = 60, (0.0, 12.0)
+    count, _ = c_oracle.rdf_single_frame(a, b, list(L) + [90, 90, 90], nbins, rng)
+    ta = cKDTree(a.astype(np.float64), boxsize=L)
+    tb = cKDTree(b.astype(np.float64), boxsize=L)
+    sp = ta.sparse_distance_matrix(tb, rng[1] + 1e-3, output_type="ndarray")
+    edges = np.histogram([-1], bins=nbins, range=rng)[1]
+    _hist_agrees_up_to_edge_ties(count, sp["v"], edges, 1e-4)
+
+
+@pytest.mark.parametrize("dims", [
+    [30.0, 32.0, 34.0, 80.0, 75.0, 70.0],
+    [36.0, 36.0, 36.0, 60.0, 60.0, 90.0],
+])
+def test_triclinic_histogram_against_lattice_image_search(dims):
+    """independent implementation: float64 minimum over 125 lattice images
+    (a superset of the reference's 27) for atoms inside the cell"""
+    from pmda_b200 import mdamath, synthetic
+    gen = np.random.default_rng(13)
+    pos = synthetic.uniform_triclinic(1, 500, dims, gen)[0]
+    a, b = pos[:200], pos[200:]
+    nbins, rng = 50, (0.0, 10.0)
+    count, _ = c_oracle.rdf_single_frame(a, b, dims, nbins, rng)
+    m = mdamath.triclinic_vectors(dims, dtype=np.float64)
+    dx = b[None].astype(np.float64) - a[:, None].astype(np.float64)
+    best = np.full(dx.shape[:2], np.inf)
+    for i in range(-2, 3):
+        for j in range(-2, 3):
+            for k in range(-2, 3):
+                s = dx + i * m[0] + j * m[1] + k * m[2]
+                best = np.minimum(best, np.einsum("ijk,ijk->ij", s, s))
+    d = np.sqrt(best).ravel()
+    edges = np.histogram([-1], bins=nbins, range=rng)[1]
+    _hist_agrees_up_to_edge_ties(count, d[d <= rng[1] + 1e-3], edges, 1e-4)
