@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RDFK_VERSION 100
+#define RDFK_VERSION 110
 
 #define RDFK_OK 0
 #define RDFK_EINVAL -1    /* bad argument                                   */
@@ -105,6 +105,37 @@ int rdfk_rdf_sites(const float *xyz, int F, int natoms, const int *idxA,
                    long long total_cells, int boxkind, const float *box,
                    double r0, double r1, int nbins, const double *edges,
                    unsigned int *count, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Contacts frame kernel (the sibling analysis on the same
+ * distance arithmetic).  Replaces, for F frames at once, the body of
+ * pmda/contacts.py:270-289 (Contacts._single_frame) for ONE reference pair:
+ *   d = distance_array(grA.positions, grB.positions)      (no box)
+ *   r = d[initial_contacts]
+ *   y = fraction_contacts(r, r0[initial_contacts], **kwargs)
+ * The caller passes the contact pairs as two index lists into the frame
+ * (atom idx_a[p] of grA with atom idx_b[p] of grB, row-major order of the
+ * boolean mask) and their reference distances r0[p].
+ *
+ *   method RDFK_CONTACT_HARD    out[f*out_stride] += #{p : d_p <= r0[p]}
+ *          RDFK_CONTACT_RADIUS  out[f*out_stride] += #{p : d_p <= radius}
+ *          RDFK_CONTACT_SOFT    out[f*out_stride] +=
+ *                                   sum_p 1 / (1 + exp(beta (d_p - lambda r0[p])))
+ *          RDFK_CONTACT_DIST    out[f*out_stride + p] = d_p  (for Python
+ *                               `method` callables; out_stride >= n_pairs)
+ * The host divides by the number of pairs like hard_cut_q / soft_cut_q /
+ * radius_cut_q (MDAnalysis.analysis.contacts) do.  Counts are exact integers
+ * in double; the soft sum is accumulated in double in unspecified order.
+ * ------------------------------------------------------------------------ */
+#define RDFK_CONTACT_HARD 0
+#define RDFK_CONTACT_RADIUS 1
+#define RDFK_CONTACT_SOFT 2
+#define RDFK_CONTACT_DIST 3
+
+int rdfk_contacts(const float *xyz, int F, int natoms, const int *idx_a,
+                  const int *idx_b, const double *r0, int n_pairs, int method,
+                  double radius, double beta, double lambda, double *out,
+                  long long out_stride, void *stream);
 
 /* ------------------------------------------------------------------------
  * Diagnostics / measurement helpers (not on the reference path).

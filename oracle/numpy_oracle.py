@@ -180,3 +180,33 @@ def rdf_s_single_frame(site_pairs, dimensions, nbins, rng):
             cnt[i1, i2, :] = np.histogram(dist[j], bins=nbins, range=rng)[0]
         out.append(cnt)
     return out, box_volume(dimensions)
+
+
+# ---------------------------------------------------------------------------
+# Contacts (pmda/contacts.py:270-289).  TEST INFRASTRUCTURE like the rest of
+# this module.
+# ---------------------------------------------------------------------------
+def distance_array_nobox(ref, conf):
+    """MDAnalysis _calc_distance_array: float32 difference conf[j] - ref[i],
+    double squares summed x, y, z, double sqrt."""
+    ref = np.ascontiguousarray(ref, dtype=np.float32)
+    conf = np.ascontiguousarray(conf, dtype=np.float32)
+    out = np.empty((len(ref), len(conf)), dtype=np.float64)
+    for i in range(len(ref)):
+        dx = (conf - ref[i]).astype(np.float64)
+        out[i] = np.sqrt((dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1]) +
+                         dx[:, 2] * dx[:, 2])
+    return out
+
+
+def contacts_single_frame(frame_no, posA, posB, initial_contacts, r0s,
+                          fraction_contacts, fraction_kwargs):
+    """Contacts._single_frame restated (pmda/contacts.py:270-289)"""
+    d = distance_array_nobox(posA, posB)
+    y = np.empty(len(r0s) + 1)
+    y[0] = frame_no
+    for i, (init, r0) in enumerate(zip(initial_contacts, r0s)):
+        y[i + 1] = fraction_contacts(d[init], r0[init], **fraction_kwargs)
+    if len(y) == 1:
+        y = y[0]
+    return y

@@ -42,6 +42,10 @@ def _declare(L):
         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
         c_void_p, c_int, c_ll, c_int, c_void_p, c_double, c_double, c_int,
         c_void_p, c_void_p, c_void_p]
+    L.rdfk_contacts.restype = c_int
+    L.rdfk_contacts.argtypes = [
+        c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+        c_double, c_double, c_double, c_void_p, c_ll, c_void_p]
     L.rdfk_rdf_stats.restype = c_int
     L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
                                  c_void_p]
@@ -54,6 +58,7 @@ def _declare(L):
 #: every symbol include/rdfk.h declares
 EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
+           "rdfk_contacts",
            "rdfk_rdf_stats", "rdfk_launch_count", "rdfk_measure_fp32_peak")
 
 
@@ -115,6 +120,17 @@ def rdf_sites(xyz, F, natoms, idx_a, idx_b, off_a, off_b, cell_off, n_sites,
         _ptr(off_b), _ptr(cell_off), int(n_sites), int(total_cells),
         int(boxkind), _ptr(box), float(r0), float(r1), int(nbins), _ptr(edges),
         _ptr(count), ctypes.c_void_p(int(stream))))
+
+
+CONTACT_HARD, CONTACT_RADIUS, CONTACT_SOFT, CONTACT_DIST = 0, 1, 2, 3
+
+
+def contacts(xyz, F, natoms, idx_a, idx_b, r0, n_pairs, method, radius, beta,
+             lam, out, out_stride, stream):
+    check(lib().rdfk_contacts(
+        _ptr(xyz), int(F), int(natoms), _ptr(idx_a), _ptr(idx_b), _ptr(r0),
+        int(n_pairs), int(method), float(radius), float(beta), float(lam),
+        _ptr(out), int(out_stride), ctypes.c_void_p(int(stream))))
 
 
 def rdf_stats(workspace, stream):

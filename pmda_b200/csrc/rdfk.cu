@@ -935,7 +935,7 @@ constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
 constexpr int NSTAGE = 32;    // staged j-groups per warp (one test round)
 constexpr int PAIRS_PER_GROUP = GJ * RI;   // per lane
 static_assert(QS >= 2 * PAIRS_PER_GROUP, "queue must absorb one group");
-constexpr int DW = 8;         // queue entries per lane in flight in the drain
+constexpr int DW = 16;        // queue entries per lane in flight in the drain
 static_assert(QS <= 64 && QS % DW == 0, "fail mask is 64 bits; drain is DW-wide");
 
 constexpr int SM_Q = QS * 32 * 4;              // bytes per warp: queue
@@ -1677,6 +1677,55 @@ __global__ __launch_bounds__(256) void sites_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// Contacts (pmda/contacts.py:270-289): for every frame, the distances of the
+// contact pairs that exist in the reference conformation --
+//   d = distance_array(grA.positions, grB.positions)[initial_contacts]
+// (no box; float32 difference, double squares / sum / sqrt, MDAnalysis
+// _calc_distance_array) -- reduced per frame:
+//   METHOD 0  hard_cut_q   : number of pairs with d <= r0[pair]
+//   METHOD 1  radius_cut_q : number of pairs with d <= radius
+//   METHOD 2  soft_cut_q   : sum of 1 / (1 + exp(beta (d - lambda r0[pair])))
+//   METHOD 3  the distances themselves (for user-supplied `method` callables)
+// One thread per (frame, pair).  Counts are exact integers carried in double.
+// ---------------------------------------------------------------------------
+template <int METHOD>
+__global__ __launch_bounds__(256) void contacts_kernel(
+    const float *__restrict__ xyz, int natoms, const int *__restrict__ ia,
+    const int *__restrict__ ib, const double *__restrict__ r0, int n_pairs,
+    double radius, double beta, double lambda, double *__restrict__ out,
+    long long out_stride) {
+  const int f = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (p < n_pairs) {
+    const float *a = xyz + ((size_t)f * natoms + ia[p]) * 3;
+    const float *b = xyz + ((size_t)f * natoms + ib[p]) * 3;
+    const double dx = (double)__fsub_rn(b[0], a[0]);
+    const double dy = (double)__fsub_rn(b[1], a[1]);
+    const double dz = (double)__fsub_rn(b[2], a[2]);
+    const double d = __dsqrt_rn(__dadd_rn(
+        __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    if (METHOD == 0) v = (d <= r0[p]) ? 1.0 : 0.0;
+    else if (METHOD == 1) v = (d <= radius) ? 1.0 : 0.0;
+    else if (METHOD == 2)
+      v = 1.0 / (1.0 + exp(__dmul_rn(beta, __dsub_rn(d, __dmul_rn(lambda, r0[p])))));
+    else out[(size_t)f * out_stride + p] = d;
+  }
+  if (METHOD != 3) {
+    __shared__ double s_part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += s_part[w];
+      if (s != 0.0) atomicAdd(out + (size_t)f * out_stride, s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // FP32 peak probe: 8 independent FFMA chains per thread, no memory traffic.
 // ---------------------------------------------------------------------------
 __global__ __launch_bounds__(256) void ffma_peak_kernel(float *out, int iters,
@@ -1971,6 +2020,53 @@ extern "C" int rdfk_rdf_sites(const float *xyz, int F, int natoms,
       sites_kernel<RDFK_BOX_TRI><<<grid, 256, 0, st>>>(
           xyz, natoms, idxA, idxB, offA, offB, cell_off, n_sites, total_cells,
           box, hp, count);
+  }
+  COUNT_LAUNCH(1);
+  CUDA_TRY(cudaGetLastError());
+  return RDFK_OK;
+}
+
+extern "C" int rdfk_contacts(const float *xyz, int F, int natoms,
+                             const int *idx_a, const int *idx_b,
+                             const double *r0, int n_pairs, int method,
+                             double radius, double beta, double lambda,
+                             double *out, long long out_stride, void *stream) {
+  if (F < 0 || natoms < 0 || n_pairs < 0)
+    return set_err(RDFK_EINVAL, "negative size%s%s");
+  if (method < RDFK_CONTACT_HARD || method > RDFK_CONTACT_DIST)
+    return set_err(RDFK_EINVAL, "bad contact method%s%s");
+  if (F == 0 || n_pairs == 0) return RDFK_OK;
+  if (!xyz || !idx_a || !idx_b || !out ||
+      ((method == RDFK_CONTACT_HARD || method == RDFK_CONTACT_SOFT) && !r0))
+    return set_err(RDFK_EINVAL, "null pointer argument%s%s");
+  if (F > 65535) return set_err(RDFK_EINVAL, "at most 65535 frames per call%s%s");
+  if (method == RDFK_CONTACT_DIST ? out_stride < n_pairs : out_stride < 1)
+    return set_err(RDFK_EINVAL, "out_stride too small%s%s");
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((n_pairs + 255) / 256), (unsigned)F);
+  switch (method) {
+    case RDFK_CONTACT_HARD:
+      contacts_kernel<0><<<grid, 256, 0, st>>>(xyz, natoms, idx_a, idx_b, r0,
+                                               n_pairs, radius, beta, lambda,
+                                               out, out_stride);
+      break;
+    case RDFK_CONTACT_RADIUS:
+      contacts_kernel<1><<<grid, 256, 0, st>>>(xyz, natoms, idx_a, idx_b, r0,
+                                               n_pairs, radius, beta, lambda,
+                                               out, out_stride);
+      break;
+    case RDFK_CONTACT_SOFT:
+      contacts_kernel<2><<<grid, 256, 0, st>>>(xyz, natoms, idx_a, idx_b, r0,
+                                               n_pairs, radius, beta, lambda,
+                                               out, out_stride);
+      break;
+    default:
+      contacts_kernel<3><<<grid, 256, 0, st>>>(xyz, natoms, idx_a, idx_b, r0,
+                                               n_pairs, radius, beta, lambda,
+                                               out, out_stride);
   }
   COUNT_LAUNCH(1);
   CUDA_TRY(cudaGetLastError());

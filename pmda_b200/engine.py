@@ -69,6 +69,7 @@ class CudaBackend(object):
     rdf_workspace_bytes = staticmethod(_cabi.rdf_workspace_bytes)
     rdf_hist = staticmethod(_cabi.rdf_hist)
     rdf_sites = staticmethod(_cabi.rdf_sites)
+    contacts = staticmethod(_cabi.contacts)
 
 
 _backend = CudaBackend()
@@ -786,3 +787,106 @@ def run_rdf_s_blocks(traj, natoms, site, blocks, nbins, rng, edges, n_jobs):
 
     return _finish(cnt_np, extra[0], extra[1], extra[2], first, blocks,
                    make_result)
+
+
+# --------------------------------------------------------------------------
+# Contacts (per-frame time series instead of an accumulated histogram)
+# --------------------------------------------------------------------------
+def _run_contacts_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
+    st = _state(device)
+    be = _backend
+    width = spec["width"]
+    out = {
+        "hist": None,
+        "vol": np.zeros(n_frames, dtype=np.float64),
+        "io": np.zeros(n_frames, dtype=np.float64),
+        "compute": np.zeros(n_frames, dtype=np.float64),
+        "first_launch": np.full(n_blocks, np.inf),
+    }
+    with st.lock:
+        cuda = st.is_cuda
+        ctx = torch.cuda.device(device) if cuda else _nullctx()
+        with ctx:
+            # one row per frame of the run (frames of other devices stay 0)
+            series = torch.zeros((n_frames, width), dtype=torch.float64,
+                                 device=device)
+            refs = []
+            for ref in spec["refs"]:
+                refs.append((_to_dev_i32(ref["ia"], device),
+                             _to_dev_i32(ref["ib"], device),
+                             torch.as_tensor(ref["r0"], dtype=torch.float64,
+                                             device=device),
+                             len(ref["ia"]), ref["col"]))
+            pipe = _Pipeline(st, traj, natoms)
+            if spec["method"] == _cabi.CONTACT_DIST:
+                # keep batches of emitted distances bounded (256 MB)
+                cap = max(1, (256 << 20) // max(8, 8 * width))
+                pipe.batch_frames = max(1, min(pipe.batch_frames, cap))
+            timers = []
+            if cuda:
+                st.compute_stream.wait_stream(torch.cuda.current_stream(device))
+            for (b, pos0, frames) in segs:
+                done = 0
+                for batch in pipe.batches(frames):
+                    B = len(batch)
+                    xyz, dims, t_io, slot = pipe.fetch(batch)
+                    lo_f = pos0 + done
+                    out["io"][lo_f:lo_f + B] = t_io / B
+                    out["first_launch"][b] = min(out["first_launch"][b],
+                                                 time.time())
+                    tm = _Timer(st)
+                    tm.start()
+                    stream = st.compute_stream.cuda_stream if cuda else 0
+                    for (ia, ib, r0, npairs, col) in refs:
+                        be.contacts(xyz, B, natoms, ia, ib, r0, npairs,
+                                    spec["method"], spec["radius"],
+                                    spec["beta"], spec["lambda"],
+                                    series[lo_f:lo_f + B, col:], width, stream)
+                    tm.stop()
+                    pipe.mark_compute_done(slot)
+                    timers.append((tm, lo_f, B))
+                    done += B
+            for tm, lo_f, B in timers:
+                out["compute"][lo_f:lo_f + B] = tm.seconds() / B
+            if cuda:
+                st.compute_stream.synchronize()
+            out["hist"] = series
+    return out
+
+
+def run_contacts_blocks(traj, natoms, spec, blocks, n_jobs):
+    """Contacts over frame blocks.  ``spec``: ``refs`` = list of dicts with the
+    contact pairs of one reference (``ia``, ``ib`` absolute atom indices,
+    ``r0`` float64, ``col`` = first output column), ``method`` (rdfk.h
+    RDFK_CONTACT_*), ``radius``, ``beta``, ``lambda``, ``width`` = columns per
+    frame.  -> per-block tuples whose first element is the float64
+    ``[n_frames_of_block, width]`` array of per-frame sums / distances."""
+    devices = _backend.devices(n_jobs)
+    n_blocks = len(blocks)
+    parts, n_frames = _shard_for_this_rank(blocks, devices)
+
+    def fn(device, segs):
+        return _run_contacts_part(device, traj, natoms, segs, n_blocks,
+                                  n_frames, spec)
+
+    outs = _run_parts(fn, devices, parts)
+    series = _combine(outs, devices[0], n_frames, spec["width"],
+                      torch.float64)
+    series = _allreduce(series)          # every frame was computed by one rank
+    extra = np.stack([sum(o["vol"] for o in outs),
+                      sum(o["io"] for o in outs),
+                      sum(o["compute"] for o in outs)])
+    if _dist_world() > 1:
+        extra = _allreduce(torch.from_numpy(extra)).numpy()
+    first = np.min(np.stack([o["first_launch"] for o in outs]), axis=0)
+    series_np = series.cpu().numpy()
+    res, pos = [], 0
+    for b, blk in enumerate(blocks):
+        n = len(blk)
+        t_io = extra[1][pos:pos + n].copy()
+        t_c = extra[2][pos:pos + n].copy()
+        wait_end = first[b] if np.isfinite(first[b]) else time.time()
+        res.append((series_np[pos:pos + n].copy(), t_io, t_c, 0.0, wait_end,
+                    np.sum(t_io), np.sum(t_c)))
+        pos += n
+    return res

@@ -74,3 +74,22 @@ class OracleBackend(object):
                                        b, float(r1), float(r0), float(r1),
                                        int(nbins), e, view)
         count += torch.from_numpy(dense.reshape(-1).astype(np.int32))
+
+    def contacts(self, xyz, F, natoms, idx_a, idx_b, r0, n_pairs, method,
+                 radius, beta, lam, out, out_stride, stream):
+        self.calls += 1
+        pos = xyz.numpy()
+        a, b = idx_a.numpy(), idx_b.numpy()
+        r0 = None if r0 is None else r0.numpy()
+        for f in range(F):
+            dx = (pos[f][b] - pos[f][a]).astype(np.float64)   # float32 diff
+            d = np.sqrt((dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1]) +
+                        dx[:, 2] * dx[:, 2])
+            if method == 0:
+                out[f, 0] += float((d <= r0).sum())
+            elif method == 1:
+                out[f, 0] += float((d <= radius).sum())
+            elif method == 2:
+                out[f, 0] += float((1 / (1 + np.exp(beta * (d - lam * r0)))).sum())
+            else:
+                out[f, :n_pairs] = torch.from_numpy(d)

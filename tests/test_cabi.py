@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = _cabi.lib()
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.rdfk_version() == 100
+    assert lib.rdfk_version() == 110
 
 
 def test_argument_validation_needs_no_gpu():
