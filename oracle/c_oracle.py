@@ -43,6 +43,11 @@ def lib():
             _f32p, ctypes.c_int64, _f32p, ctypes.c_int64, ctypes.c_int, _f32p,
             ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
             _f64p, ctypes.c_int, ctypes.c_int, _i64p, ctypes.c_int]
+        L.oracle_rdf_frame_cells.restype = ctypes.c_int
+        L.oracle_rdf_frame_cells.argtypes = [
+            _f32p, ctypes.c_int64, _f32p, ctypes.c_int64, _f32p,
+            ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+            _f64p, ctypes.c_int, ctypes.c_int, _i64p, ctypes.c_int]
         L.oracle_rdf_s_frame.restype = None
         L.oracle_rdf_s_frame.argtypes = [
             _f32p, ctypes.c_int64, _f32p, ctypes.c_int64, ctypes.c_int, _f32p,
@@ -92,19 +97,28 @@ def np_bin(d, nbins, rng, edges=None):
 
 
 def rdf_single_frame(g1, g2, dimensions, nbins, rng, exclusion_block=None,
-                     count=None, nthreads=1):
+                     count=None, nthreads=1, cells=False):
     """InterRDF._single_frame -> (count int64[nbins], volume); accumulates
-    into `count` when given."""
+    into `count` when given.  ``cells=True``: through the cell list
+    (orthorhombic, fully periodic boxes; same integers, fewer pairs visited);
+    falls back to the full pair matrix when the box does not allow it."""
     g1, g2 = _c32(g1), _c32(g2)
     kind, b = _box_args(dimensions)
     edges = edges_of(nbins, rng)
     if count is None:
         count = np.zeros(nbins, dtype=np.int64)
     xa, xb = (0, 0) if exclusion_block is None else exclusion_block
+    vol = 0.0 if dimensions is None else float(box_volume(dimensions))
+    if cells and kind == 1:
+        rc = lib().oracle_rdf_frame_cells(
+            g1, len(g1), g2, len(g2), b, float(rng[1]), float(rng[0]),
+            float(rng[1]), int(nbins), edges, int(xa), int(xb), count,
+            int(nthreads))
+        if rc == 0:
+            return count, vol
     lib().oracle_rdf_frame(g1, len(g1), g2, len(g2), kind, b, float(rng[1]),
                            float(rng[0]), float(rng[1]), int(nbins), edges,
                            int(xa), int(xb), count, int(nthreads))
-    vol = 0.0 if dimensions is None else float(box_volume(dimensions))
     return count, vol
 
 

@@ -274,6 +274,115 @@ void oracle_rdf_frame(const float *g1, int64_t n1, const float *g2,
 }
 
 /* ------------------------------------------------------------------------ */
+/* The same frame through a cell list (orthorhombic boxes, all axes          */
+/* periodic): what MDAnalysis' capped_distance does on the CPU when it       */
+/* dispatches to its grid search instead of distance_array                   */
+/* (lib/distances.py _determine_method: N1*N2 >= 1e8, call site              */
+/* pmda/rdf.py:123).  Every pair within reach is evaluated with exactly the  */
+/* arithmetic above, so the counts equal oracle_rdf_frame's; only pairs in   */
+/* cells further than one cell (edge >= 1.001 * max_cutoff) apart are        */
+/* skipped.  Used as the faster CPU baseline of bench.py and as a cross      */
+/* check of the pruning idea.  Returns 0, or -1 when the box does not allow  */
+/* a cell list (the caller then uses oracle_rdf_frame).                      */
+/* ------------------------------------------------------------------------ */
+int oracle_rdf_frame_cells(const float *g1, int64_t n1, const float *g2,
+                           int64_t n2, const float *box, double max_cutoff,
+                           double r0, double r1, int nbins,
+                           const double *edges, int excl_a, int excl_b,
+                           int64_t *count, int nthreads) {
+  int nc[3];
+  for (int k = 0; k < 3; k++) {
+    if (!(box[k] > FLT_EPSILON)) return -1;
+    double m = floor((double)box[k] / (max_cutoff * 1.001 + 1e-6));
+    if (m < 1.0) m = 1.0;
+    if (m > 512.0) m = 512.0;
+    nc[k] = (int)m;
+  }
+  float inv[3];
+  make_inverse_box(box, inv);
+  const int64_t ncell = (int64_t)nc[0] * nc[1] * nc[2];
+  int64_t *start = (int64_t *)calloc((size_t)ncell + 1, sizeof(int64_t));
+  int64_t *cell_of = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n2 > 0 ? n2 : 1));
+  int64_t *order = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n2 > 0 ? n2 : 1));
+  int bad = 0;
+  for (int64_t j = 0; j < n2; j++) {
+    int c[3];
+    for (int k = 0; k < 3; k++) {
+      double f = (double)g2[3 * j + k] / (double)box[k];
+      f -= floor(f);
+      if (!(f >= 0.0 && f <= 1.0)) { bad = 1; f = 0.0; }   /* NaN / Inf */
+      int ci = (int)(f * nc[k]);
+      c[k] = ci >= nc[k] ? nc[k] - 1 : ci;
+    }
+    cell_of[j] = ((int64_t)c[0] * nc[1] + c[1]) * nc[2] + c[2];
+    start[cell_of[j] + 1]++;
+  }
+  if (bad) { free(start); free(cell_of); free(order); return -1; }
+  for (int64_t c = 0; c < ncell; c++) start[c + 1] += start[c];
+  {
+    int64_t *fill = (int64_t *)malloc(sizeof(int64_t) * (size_t)ncell);
+    memcpy(fill, start, sizeof(int64_t) * (size_t)ncell);
+    for (int64_t j = 0; j < n2; j++) order[fill[cell_of[j]]++] = j;
+    free(fill);
+  }
+  if (nthreads < 1) nthreads = 1;
+  int fail = 0;
+#pragma omp parallel num_threads(nthreads)
+  {
+    int64_t *local = (int64_t *)calloc((size_t)nbins, sizeof(int64_t));
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n1; i++) {
+      int c[3], ok = 1;
+      for (int k = 0; k < 3; k++) {
+        double f = (double)g1[3 * i + k] / (double)box[k];
+        f -= floor(f);
+        if (!(f >= 0.0 && f <= 1.0)) { ok = 0; f = 0.0; }
+        int ci = (int)(f * nc[k]);
+        c[k] = ci >= nc[k] ? nc[k] - 1 : ci;
+      }
+      if (!ok) {
+#pragma omp atomic write
+        fail = 1;
+        continue;
+      }
+      /* distinct neighbour cells along each axis (fewer than 3 cells: all) */
+      int nb[3][3], nn[3];
+      for (int k = 0; k < 3; k++) {
+        if (nc[k] < 3) {
+          nn[k] = nc[k];
+          for (int t = 0; t < nc[k]; t++) nb[k][t] = t;
+        } else {
+          nn[k] = 3;
+          for (int t = 0; t < 3; t++) nb[k][t] = (c[k] + t - 1 + nc[k]) % nc[k];
+        }
+      }
+      for (int a = 0; a < nn[0]; a++)
+        for (int b = 0; b < nn[1]; b++)
+          for (int e = 0; e < nn[2]; e++) {
+            const int64_t cell = ((int64_t)nb[0][a] * nc[1] + nb[1][b]) * nc[2] + nb[2][e];
+            for (int64_t t = start[cell]; t < start[cell + 1]; t++) {
+              const int64_t j = order[t];
+              double d = pair_distance(g1 + 3 * i, g2 + 3 * j, ORACLE_BOX_ORTHO,
+                                       box, inv);
+              if (!(d <= max_cutoff)) continue;
+              if (excl_a > 0 && excl_b > 0 && (i / excl_a) == (j / excl_b)) continue;
+              int k = oracle_np_bin(d, r0, r1, nbins, edges);
+              if (k >= 0) local[k] += 1;
+            }
+          }
+    }
+#pragma omp critical
+    if (!fail)
+      for (int k = 0; k < nbins; k++) count[k] += local[k];
+    free(local);
+  }
+  free(start);
+  free(cell_of);
+  free(order);
+  return fail ? -1 : 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* InterRDF_s._single_frame for ONE site pair (pmda/rdf.py:296-305):         */
 /*   count[idx1, idx2, :] = one-hot histogram of dist for every in-range     */
 /*   (idx1, idx2).  `count` is double [n1][n2][nbins]; this ADDS the one-hot */

@@ -125,3 +125,29 @@ def test_invalid_box_vectors_are_zero():
     assert not mdamath.triclinic_vectors([10, 10, 10, 10, 20, 170]).any()
     assert not mdamath.triclinic_vectors([10, -1, 10, 90, 90, 90]).any()
     assert mdamath.box_volume([10, 10, 10, 10, 20, 170]) == 0.0
+
+
+@pytest.mark.parametrize("L,n,rmax", [
+    ((40.0, 44.0, 38.0), 3000, 9.0),     # several cells per axis
+    ((20.0, 50.0, 30.0), 2500, 9.5),     # two / five / three cells
+    ((16.0, 17.0, 15.5), 1200, 9.0),     # one cell per axis: every pair
+])
+def test_cell_list_oracle_equals_full_pair_matrix(L, n, rmax):
+    """oracle_rdf_frame_cells (the faster CPU baseline) must give the integers
+    of the O(N1 N2) oracle, also for unwrapped coordinates and exclusions"""
+    gen = np.random.default_rng(31)
+    Lv = np.array(L)
+    pos = (gen.random((n, 3)) * Lv * 3 - Lv).astype(np.float32)   # unwrapped
+    dims = list(L) + [90, 90, 90]
+    a, b = pos[: n // 3], pos
+    for excl in (None, (3, 5)):
+        full, _ = c_oracle.rdf_single_frame(a, b, dims, 60, (0.0, rmax), excl,
+                                            nthreads=4)
+        cell, _ = c_oracle.rdf_single_frame(a, b, dims, 60, (0.0, rmax), excl,
+                                            nthreads=4, cells=True)
+        np.testing.assert_array_equal(cell, full)
+    # partial PBC: no cell list, silently the full matrix
+    dims0 = [L[0], L[1], 0.0, 90, 90, 90]
+    full, _ = c_oracle.rdf_single_frame(a, b, dims0, 40, (0.0, rmax))
+    cell, _ = c_oracle.rdf_single_frame(a, b, dims0, 40, (0.0, rmax), cells=True)
+    np.testing.assert_array_equal(cell, full)
