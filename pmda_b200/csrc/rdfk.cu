@@ -408,10 +408,12 @@ __global__ __launch_bounds__(256) void stage_kernel(
     o[(size_t)npad + a] = y;
     o[2 * (size_t)npad + a] = z;
   }
-  // per-frame extents (fminf/fmaxf drop NaN)
+  // per-frame extents (fminf/fmaxf drop NaN): warp shuffle, then one set of
+  // atomics per CTA (same-address global atomics serialise)
   const float big = FLT_MAX;
   float mn[3] = {valid ? x : big, valid ? y : big, valid ? z : big};
   float mx[3] = {valid ? x : -big, valid ? y : -big, valid ? z : -big};
+  __shared__ float s_mn[8][3], s_mx[8][3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     // a NaN / Inf coordinate must poison the extents (-> all_slow frame)
@@ -423,14 +425,22 @@ __global__ __launch_bounds__(256) void stage_kernel(
       mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
       mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
     }
-  }
-  if ((threadIdx.x & 31) == 0) {
-    int *e = extents + f * 6;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (mn[k] < big) atomicMin(e + k, float_to_ordered(mn[k]));
-      if (mx[k] > -big) atomicMax(e + 3 + k, float_to_ordered(mx[k]));
+    if ((threadIdx.x & 31) == 0) {
+      s_mn[threadIdx.x >> 5][k] = mn[k];
+      s_mx[threadIdx.x >> 5][k] = mx[k];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int k = threadIdx.x;
+    float lo = big, hi = -big;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      lo = fminf(lo, s_mn[w][k]);
+      hi = fmaxf(hi, s_mx[w][k]);
+    }
+    int *e = extents + f * 6;
+    if (lo < big) atomicMin(e + k, float_to_ordered(lo));
+    if (hi > -big) atomicMax(e + 3 + k, float_to_ordered(hi));
   }
 }
 
