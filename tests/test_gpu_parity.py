@@ -209,3 +209,24 @@ def test_interrdf_s_triclinic():
     counts, volume, nf = oracle_interrdf_s(u, ags)
     for s in range(2):
         np.testing.assert_array_equal(r.count[s], counts[s])
+
+
+def test_two_local_gpus_give_the_same_integers():
+    """n_jobs = 2: frames sharded over two devices of this process"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(24)
+    L = 50.0
+    pos = (rng.random((9, 8000, 3)) * L).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    one = InterRDF(u.atoms, u.atoms).run(n_jobs=1, n_blocks=3)
+    two = InterRDF(u.atoms, u.atoms).run(n_jobs=2, n_blocks=3)
+    np.testing.assert_array_equal(two.count, one.count)
+    np.testing.assert_array_equal(two.rdf, one.rdf)
+    assert len(two._results) == 3
+    ags = [[u.atoms[[0]], u.atoms[1:200]], [u.atoms[[5, 6]], u.atoms[300:350]]]
+    s1 = InterRDF_s(u, ags).run(n_jobs=1)
+    s2 = InterRDF_s(u, ags).run(n_jobs=2, n_blocks=2)
+    for a, b in zip(s1.count, s2.count):
+        np.testing.assert_array_equal(a, b)
