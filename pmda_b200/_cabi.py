@@ -67,9 +67,20 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RdfkError(
-                "CUDA extension %s is missing: run `python -m "
-                "pmda_b200.csrc.build` (there is no CPU fallback)" % LIB_PATH)
+            # not built yet (fresh checkout): compile the same CUDA sources
+            # with nvcc if the toolchain is here; never a CPU substitute
+            why = "not built"
+            try:
+                from .csrc import build as _build
+                if os.path.abspath(_build.OUT) == os.path.abspath(LIB_PATH):
+                    _build.build()
+            except Exception as exc:        # no nvcc, compile error, ...
+                why = str(exc)
+            if not os.path.exists(LIB_PATH):
+                raise RdfkError(
+                    "CUDA extension %s is missing (%s): run `python -m "
+                    "pmda_b200.csrc.build` (there is no CPU fallback)"
+                    % (LIB_PATH, why))
         L = ctypes.CDLL(LIB_PATH)
         _declare(L)
         _lib = L
