@@ -1311,7 +1311,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                          : "r"(tab_s32 + 8u * tidx));
           }
           const bool act = rem > u;
-          const bool inband = r2 >= t.x && r2 < t.y;
+          const bool inband = (r2 >= t.x) & (r2 < t.y);
           if (GLOBAL_HIST) {
             if (act && inband && k >= 0)
               atomicAdd(a.hist + k, (unsigned long long)weight);
@@ -1407,44 +1407,54 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         // two pairs; j-atom pairs come straight out of the LDS.128 registers,
         // the i-atom is a broadcast scalar operand.  Quarters that cannot
         // reach the group are skipped (warp-uniform).
+        // The group is read from shared memory once (6 LDS.128), not once per
+        // quarter: the shared-memory pipe is the kernel's co-bottleneck
+        // (65 % of peak wavefronts, profiles/r1_notes.md).
+        const ulonglong2 X0 = *reinterpret_cast<const ulonglong2 *>(js);
+        const ulonglong2 X1 = *reinterpret_cast<const ulonglong2 *>(js + 4);
+        const ulonglong2 Y0 = *reinterpret_cast<const ulonglong2 *>(js + GJ);
+        const ulonglong2 Y1 = *reinterpret_cast<const ulonglong2 *>(js + GJ + 4);
+        const ulonglong2 Z0 = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ);
+        const ulonglong2 Z1 = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ + 4);
+        const uint64_t xj2[4] = {X0.x, X0.y, X1.x, X1.y};
+        const uint64_t yj2[4] = {Y0.x, Y0.y, Y1.x, Y1.y};
+        const uint64_t zj2[4] = {Z0.x, Z0.y, Z1.x, Z1.y};
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
           if (!((qmask >> r) & 1)) continue;
           const uint64_t nx2 = pk2(nxs[r], nxs[r]), ny2 = pk2(nys[r], nys[r]),
                          nz2 = pk2(nzs[r], nzs[r]);
 #pragma unroll
-          for (int up = 0; up < GJ / 2; up += 2) {
-            const ulonglong2 X = *reinterpret_cast<const ulonglong2 *>(js + 2 * up);
-            const ulonglong2 Y = *reinterpret_cast<const ulonglong2 *>(js + GJ + 2 * up);
-            const ulonglong2 Z = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ + 2 * up);
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              const uint64_t dx = add2(h2 ? X.y : X.x, nx2),
-                             dy = add2(h2 ? Y.y : Y.x, ny2),
-                             dz = add2(h2 ? Z.y : Z.x, nz2);
-              const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-              float ra, rb;
-              unpk2(t, ra, rb);
-              q_push(qaddr, ra, cut);
-              q_push(qaddr, rb, cut);
-            }
+          for (int up = 0; up < GJ / 2; ++up) {
+            const uint64_t dx = add2(xj2[up], nx2), dy = add2(yj2[up], ny2),
+                           dz = add2(zj2[up], nz2);
+            const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float ra, rb;
+            unpk2(t, ra, rb);
+            q_push(qaddr, ra, cut);
+            q_push(qaddr, rb, cut);
           }
         }
       } else {
         // per-pair minimum image (ortho rint / triclinic brick), same order
+        const float4 Xa = *reinterpret_cast<const float4 *>(js);
+        const float4 Xb = *reinterpret_cast<const float4 *>(js + 4);
+        const float4 Ya = *reinterpret_cast<const float4 *>(js + GJ);
+        const float4 Yb = *reinterpret_cast<const float4 *>(js + GJ + 4);
+        const float4 Za = *reinterpret_cast<const float4 *>(js + 2 * GJ);
+        const float4 Zb = *reinterpret_cast<const float4 *>(js + 2 * GJ + 4);
+        const float xj8[GJ] = {Xa.x, Xa.y, Xa.z, Xa.w, Xb.x, Xb.y, Xb.z, Xb.w};
+        const float yj8[GJ] = {Ya.x, Ya.y, Ya.z, Ya.w, Yb.x, Yb.y, Yb.z, Yb.w};
+        const float zj8[GJ] = {Za.x, Za.y, Za.z, Za.w, Zb.x, Zb.y, Zb.z, Zb.w};
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
           if (!((qmask >> r) & 1)) continue;
 #pragma unroll
-          for (int u4 = 0; u4 < GJ; u4 += 4) {
-            const float4 X = *reinterpret_cast<const float4 *>(js + u4);
-            const float4 Y = *reinterpret_cast<const float4 *>(js + GJ + u4);
-            const float4 Z = *reinterpret_cast<const float4 *>(js + 2 * GJ + u4);
-            q_push(qaddr, pair_r2<BOXKIND, false>(X.x, Y.x, Z.x, nxs[r], nys[r], nzs[r], fb), cut);
-            q_push(qaddr, pair_r2<BOXKIND, false>(X.y, Y.y, Z.y, nxs[r], nys[r], nzs[r], fb), cut);
-            q_push(qaddr, pair_r2<BOXKIND, false>(X.z, Y.z, Z.z, nxs[r], nys[r], nzs[r], fb), cut);
-            q_push(qaddr, pair_r2<BOXKIND, false>(X.w, Y.w, Z.w, nxs[r], nys[r], nzs[r], fb), cut);
-          }
+          for (int u = 0; u < GJ; ++u)
+            q_push(qaddr,
+                   pair_r2<BOXKIND, false>(xj8[u], yj8[u], zj8[u], nxs[r], nys[r],
+                                           nzs[r], fb),
+                   cut);
         }
       }
     };
