@@ -1290,7 +1290,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         float v[DW];
 #pragma unroll
         for (int u = 0; u < DW; ++u) v[u] = q[(s + u) * 32 + lane];
-        unsigned int fail = 0u;
+        unsigned int okmask = 0u;
         const int rem = n - s;   // entries s .. s + rem - 1 are live
 #pragma unroll
         for (int u = 0; u < DW; ++u) {
@@ -1310,22 +1310,26 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                          : "=f"(t.x), "=f"(t.y)
                          : "r"(tab_s32 + 8u * tidx));
           }
-          const bool act = rem > u;
-          const bool inband = (r2 >= t.x) & (r2 < t.y);
+          // live and certainly in bin k (one predicate chain, no branches)
+          const bool ok = (rem > u) & (r2 >= t.x) & (r2 < t.y);
           if (GLOBAL_HIST) {
-            if (act && inband && k >= 0)
+            if (ok && k >= 0)
               atomicAdd(a.hist + k, (unsigned long long)weight);
           } else {
             // unconditional: inactive / failed entries go to this lane's own
             // dummy word (same-address atomics of one warp serialise), k == -1
             // ("certainly below r0") to the dummy slot in front of the copy
-            const uint32_t ha = (act && inband) ? wh_s + 4u * (unsigned int)k
-                                                : dummy_s;
+            const uint32_t ha = ok ? wh_s + 4u * (unsigned int)k : dummy_s;
             asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ha), "r"(weight)
                          : "memory");
           }
-          if (act && !inband) fail |= 1u << u;
+          okmask |= (unsigned int)ok << u;
         }
+        // live entries that were not certain need the fp64 path
+        const unsigned int livemask =
+            rem >= DW ? (unsigned int)((1ull << DW) - 1ull)
+                      : ((1u << (rem > 0 ? rem : 0)) - 1u);
+        const unsigned int fail = livemask & ~okmask;
         failmask |= (unsigned long long)fail << s;
       }
       // the rare band failures, after the pipelined loop
