@@ -111,3 +111,22 @@ def test_config5_full_size_1k_x_1m():
     rs = _run(sub, g2, nbins, rng)
     want, _, _ = oracle_interrdf(u, sub, g2, nbins, rng)
     np.testing.assert_array_equal(rs.count, want)
+
+
+def test_repeated_runs_are_bit_identical():
+    """work distribution is dynamic (atomic work counter, warp-level queues);
+    the integers must not depend on it"""
+    from pmda_b200 import engine
+    u, kw = synthetic.config2(n_frames=4, n_atoms=60_000)
+    g, nbins, rng = kw["g1"], kw["nbins"], kw["range"]
+    first = _run(g, g, nbins, rng).count
+    for rep in range(12):
+        if rep % 3 == 0:
+            engine.clear_cache()
+        again = _run(g, g, nbins, rng, n_blocks=1 + rep % 3).count
+        np.testing.assert_array_equal(again, first)
+    u4, kw4 = synthetic.config4(n_frames=2, n_atoms=40_000)
+    first = _run(kw4["g1"], kw4["g2"], kw4["nbins"], kw4["range"]).count
+    for rep in range(6):
+        again = _run(kw4["g1"], kw4["g2"], kw4["nbins"], kw4["range"]).count
+        np.testing.assert_array_equal(again, first)
