@@ -933,12 +933,12 @@ struct PairArgs {
 // them where they are found wastes the warp on divergence (measured 2.8x
 // slower, tools/ubench2.cu).  Instead every lane appends the fp32 r2 of its
 // hits to a private queue in shared memory with three predicated instructions
-// (no branch), and the warp drains all queues at warp-uniform points, four
-// entries per lane in flight.  The sign bit of an entry selects the decision
-// table (negative: shifted / minimum-image arithmetic).  The pair behind an
-// entry is implied: the warp logs the j-groups it evaluated since the last
-// drain and every lane marks its queue length at each group start, so the
-// rare band failure re-scans one group (resolve_entry).
+// (no branch), and the warp drains all queues at warp-uniform points, DW
+// entries per lane in flight.  The decision table (tight / loose class) is
+// warp-uniform because a work item is processed class by class.  The pair
+// behind an entry is implied: the warp logs the j-groups it evaluated since
+// the last drain and every lane marks its queue length at each group start,
+// so the rare band failure re-scans one group (resolve_entry).
 // ---------------------------------------------------------------------------
 constexpr int QS = 64;        // queue slots per lane
 constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
@@ -1131,6 +1131,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       GLOBAL_HIST ? nullptr : hist_s + (size_t)(warp % copies) * hstride + 1;
   const uint32_t wh_s = GLOBAL_HIST ? 0u : smem_u32(wh);
   const unsigned int sharers = GLOBAL_HIST ? 1 : (NWARP + copies - 1) / copies;
+  const unsigned int flush_limit = (1u << 30) / sharers;
   const uint32_t qbase = smem_u32(q + lane);
   uint32_t qaddr = qbase;
   const unsigned int lt_mask = (1u << lane) - 1u;
@@ -1262,7 +1263,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     float cut = cut0;
 
     auto maybe_flush = [&]() {
-      if (!GLOBAL_HIST && added > (1u << 30) / sharers) {
+      if (!GLOBAL_HIST && added > flush_limit) {
         for (int b = lane; b < nbins; b += 32) {
           const unsigned int v = atomicExch(wh + b, 0u);
           if (v) atomicAdd(a.hist + b, (unsigned long long)v);
@@ -1275,10 +1276,11 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       else atomicAdd(wh + k, weight);
     };
 
-    // bin everything queued so far.  Warp-uniform call sites only; four
-    // entries per lane in flight, no per-entry branches: the candidate bin
-    // comes from MUFU.SQRT and a magic-number round (no F2I), the tables have
-    // a "drop" entry in front, inactive slots go to a dummy histogram slot.
+    // bin everything queued so far.  Warp-uniform call sites only; DW entries
+    // per lane in flight, no per-entry branches: the candidate bin comes from
+    // MUFU.SQRT and a magic-number round (no F2I), the tables have a "drop"
+    // entry in front, inactive / failed slots go to a per-lane dummy word,
+    // band failures are collected in a mask and resolved after the loop.
     auto drain = [&]() {
       __syncwarp();   // the group log was written by lane 0
       const int n = (int)((qaddr - qbase) >> 7);
