@@ -33,5 +33,5 @@ def test_cuda_path_matches_golden_counts(name):
         GOLD[name + "__sha256"].tobytes().decode()
     u = Universe(pos, dims)
     r = InterRDF(u.atoms[i1], u.atoms[i2], nbins=nbins, range=rng,
-                 exclusion_block=excl).run(n_blocks=2)
+                 exclusion_block=excl).run(n_blocks=min(2, len(pos)))
     np.testing.assert_array_equal(r.count, GOLD[name + "__count"])
