@@ -18,6 +18,7 @@ the host in frame order, like ``_reduce`` does in the reference.
 
 There is no CPU fallback: without the CUDA library / a GPU this raises.
 """
+import collections
 import itertools
 import os
 import threading
@@ -163,12 +164,25 @@ def _traj_token(traj):
     return tok
 
 
+# Finalizers can run at any allocation (garbage collection), i.e. also while
+# this very thread holds _states_lock or a device lock: they must not take
+# locks.  They only record the dead token (deque.append is atomic); the cache
+# entries are purged the next time the device state is used.
+_dead_tokens = collections.deque()
+
+
 def _drop_token(tok):
-    with _states_lock:
-        for st in _states.values():
-            for key in [k for k in st.cache if k[0] == tok]:
-                _, _, nbytes = st.cache.pop(key)
-                st.cache_used -= nbytes
+    _dead_tokens.append(tok)
+
+
+def _purge_dead(st):
+    """drop the cached frame blocks of trajectories that no longer exist
+    (caller holds ``st.lock``)"""
+    if not _dead_tokens:
+        return
+    dead = set(_dead_tokens)
+    for key in [k for k in st.cache if k[0] in dead]:
+        st.cache_used -= st.cache.pop(key)[2]
 
 
 def _fingerprint(pos, dims):
@@ -330,6 +344,7 @@ class _Pipeline(object):
         self.pslot = 0
         self.h2d_done = [None, None]
         self.compute_done = [None, None]
+        _purge_dead(st)
         self.traj_key = _traj_token(traj)
         #: in-memory trajectories hand out views: re-reading them is free, so
         #: the cache entry is validated against the data on every hit

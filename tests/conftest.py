@@ -13,6 +13,13 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    # no test may stall a whole run: dump every thread's stack and stop after
+    # five minutes (pytest-timeout, "thread" method: also fires when the main
+    # thread is stuck inside a C call such as a CUDA synchronisation)
+    if config.pluginmanager.hasplugin("timeout"):
+        for item in items:
+            if item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(300, method="thread"))
     try:
         import torch
         has_gpu = torch.cuda.is_available()
