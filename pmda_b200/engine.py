@@ -35,7 +35,7 @@ from .util import make_balanced_slices
 
 class Config(object):
     #: raw frame bytes staged per batch (bigger = fewer launches)
-    batch_bytes = int(os.environ.get("PMDA_B200_BATCH_BYTES", 256 << 20))
+    batch_bytes = int(os.environ.get("PMDA_B200_BATCH_BYTES", 128 << 20))
     #: never more frames than this per kernel call
     max_batch_frames = int(os.environ.get("PMDA_B200_MAX_BATCH_FRAMES", 2048))
     #: device-resident frame cache budget per GPU (0 disables the cache)
