@@ -1146,6 +1146,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   unsigned int added = 0;   // upper bound of what this warp put into one bin
 
   for (;;) {
+    __syncwarp();
     int item = 0;
     if (lane == 0) item = atomicAdd(&a.header->work_counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
@@ -1385,6 +1386,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         }
         added += 2u * PAIRS_PER_GROUP * 32u;
         maybe_flush();
+        __syncwarp();   // the fp64 loops above diverge per lane
         return;
       }
       // room for this group (8 pairs per active quarter) in every lane's
