@@ -138,6 +138,18 @@ int rdfk_contacts(const float *xyz, int F, int natoms, const int *idx_a,
                   long long out_stride, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Trajectory ingest (what the reference does frame by
+ * frame in pmda/parallel.py:432-434 through MDAnalysis' DCD reader).  `raw`
+ * holds F frames exactly as they lie in a DCD file, `frame_stride` bytes
+ * apart; inside a frame the float32 planes x[natoms], y[natoms], z[natoms]
+ * start at byte offsets off_x / off_y / off_z (all multiples of 4).  Writes
+ * xyz[F][natoms][3], the layout of ts.positions the kernels above take.
+ * ------------------------------------------------------------------------ */
+int rdfk_unpack_planes(const void *raw, long long frame_stride,
+                       long long off_x, long long off_y, long long off_z,
+                       int F, int natoms, float *xyz, void *stream);
+
+/* ------------------------------------------------------------------------
  * Diagnostics / measurement helpers (not on the reference path).
  * ------------------------------------------------------------------------ */
 

@@ -9,5 +9,5 @@ how pmda itself would bind the C ABI in include/rdfk.h.
 """
 __version__ = "0.1.0"
 
-__all__ = ["rdf", "contacts", "parallel", "util", "universe", "engine",
+__all__ = ["rdf", "contacts", "parallel", "util", "universe", "dcd", "engine",
            "mdamath"]

@@ -46,6 +46,9 @@ def _declare(L):
     L.rdfk_contacts.argtypes = [
         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
         c_double, c_double, c_double, c_void_p, c_ll, c_void_p]
+    L.rdfk_unpack_planes.restype = c_int
+    L.rdfk_unpack_planes.argtypes = [c_void_p, c_ll, c_ll, c_ll, c_ll, c_int,
+                                     c_int, c_void_p, c_void_p]
     L.rdfk_rdf_stats.restype = c_int
     L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
                                  c_void_p]
@@ -58,7 +61,7 @@ def _declare(L):
 #: every symbol include/rdfk.h declares
 EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
-           "rdfk_contacts",
+           "rdfk_contacts", "rdfk_unpack_planes",
            "rdfk_rdf_stats", "rdfk_launch_count", "rdfk_measure_fp32_peak")
 
 
@@ -142,6 +145,13 @@ def contacts(xyz, F, natoms, idx_a, idx_b, r0, n_pairs, method, radius, beta,
         _ptr(xyz), int(F), int(natoms), _ptr(idx_a), _ptr(idx_b), _ptr(r0),
         int(n_pairs), int(method), float(radius), float(beta), float(lam),
         _ptr(out), int(out_stride), ctypes.c_void_p(int(stream))))
+
+
+def unpack_planes(raw, frame_stride, off_x, off_y, off_z, F, natoms, xyz,
+                  stream):
+    check(lib().rdfk_unpack_planes(
+        _ptr(raw), int(frame_stride), int(off_x), int(off_y), int(off_z),
+        int(F), int(natoms), _ptr(xyz), ctypes.c_void_p(int(stream))))
 
 
 def rdf_stats(workspace, stream):

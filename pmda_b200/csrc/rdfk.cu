@@ -1705,6 +1705,28 @@ __global__ __launch_bounds__(256) void sites_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// Trajectory ingest: frames as they lie in a DCD file (per frame three
+// Fortran records x[N], y[N], z[N] of float32, optionally preceded by a unit
+// cell record) -> the [F][N][3] layout of ts.positions that every kernel above
+// consumes.  The file bytes go to the device unchanged; this is the transpose.
+// One thread per (frame, atom): coalesced plane reads, 12-byte AoS writes.
+// ---------------------------------------------------------------------------
+__global__ __launch_bounds__(256) void unpack_planes_kernel(
+    const unsigned char *__restrict__ raw, long long frame_stride,
+    long long off_x, long long off_y, long long off_z, int natoms,
+    float *__restrict__ xyz) {
+  const int f = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= natoms) return;
+  const unsigned char *fr = raw + (size_t)f * (size_t)frame_stride;
+  const float x = reinterpret_cast<const float *>(fr + off_x)[a];
+  const float y = reinterpret_cast<const float *>(fr + off_y)[a];
+  const float z = reinterpret_cast<const float *>(fr + off_z)[a];
+  float *o = xyz + ((size_t)f * natoms + a) * 3;
+  o[0] = x; o[1] = y; o[2] = z;
+}
+
+// ---------------------------------------------------------------------------
 // Contacts (pmda/contacts.py:270-289): for every frame, the distances of the
 // contact pairs that exist in the reference conformation --
 //   d = distance_array(grA.positions, grB.positions)[initial_contacts]
@@ -2096,6 +2118,31 @@ extern "C" int rdfk_contacts(const float *xyz, int F, int natoms,
                                                n_pairs, radius, beta, lambda,
                                                out, out_stride);
   }
+  COUNT_LAUNCH(1);
+  CUDA_TRY(cudaGetLastError());
+  return RDFK_OK;
+}
+
+extern "C" int rdfk_unpack_planes(const void *raw, long long frame_stride,
+                                  long long off_x, long long off_y,
+                                  long long off_z, int F, int natoms,
+                                  float *xyz, void *stream) {
+  if (F < 0 || natoms < 0 || frame_stride < 0 || off_x < 0 || off_y < 0 ||
+      off_z < 0)
+    return set_err(RDFK_EINVAL, "negative size or offset%s%s");
+  if (F == 0 || natoms == 0) return RDFK_OK;
+  if (!raw || !xyz) return set_err(RDFK_EINVAL, "null pointer argument%s%s");
+  if (((uintptr_t)raw | (uintptr_t)frame_stride | (uintptr_t)off_x |
+       (uintptr_t)off_y | (uintptr_t)off_z) & 3u)
+    return set_err(RDFK_EINVAL, "planes must be 4-byte aligned%s%s");
+  if (F > 65535) return set_err(RDFK_EINVAL, "at most 65535 frames per call%s%s");
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  unpack_planes_kernel<<<dim3((natoms + 255) / 256, F), 256, 0, st>>>(
+      (const unsigned char *)raw, frame_stride, off_x, off_y, off_z, natoms,
+      xyz);
   COUNT_LAUNCH(1);
   CUDA_TRY(cudaGetLastError());
   return RDFK_OK;

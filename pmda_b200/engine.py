@@ -71,6 +71,7 @@ class CudaBackend(object):
     rdf_hist = staticmethod(_cabi.rdf_hist)
     rdf_sites = staticmethod(_cabi.rdf_sites)
     contacts = staticmethod(_cabi.contacts)
+    unpack_planes = staticmethod(_cabi.unpack_planes)
 
 
 _backend = CudaBackend()
@@ -105,6 +106,8 @@ class _DeviceState(object):
         self.workspace = None
         self.pinned = [None, None]
         self.staged = [None, None]
+        self.raw_pin = [None, None]      # raw file bytes (DCD blocks)
+        self.raw_dev = [None, None]
         self.cache = OrderedDict()   # key -> (xyz_dev, nbytes)
         self.cache_used = 0
         if self.is_cuda:
@@ -349,6 +352,11 @@ class _Pipeline(object):
         #: in-memory trajectories hand out views: re-reading them is free, so
         #: the cache entry is validated against the data on every hit
         self.cheap_reads = getattr(traj, "frame_block", None) is not None
+        #: file formats whose frames can go to the device as they lie on disk
+        self.raw = getattr(traj, "raw_block", None) if st.is_cuda else None
+        self.rslot = 0
+        self.raw_done = [None, None]
+        self.h2d_raw_done = [None, None]
 
     def batches(self, frames):
         """equal-sized batches of at most ``batch_frames`` frames (a short
@@ -368,6 +376,9 @@ class _Pipeline(object):
         use_cache = self.traj_key is not None and Config.cache_bytes > 0
         pos = dims = None
         key = None
+        rb = self.raw(frames) if self.raw is not None else None
+        if rb is not None:
+            return self._fetch_raw(frames, rb, use_cache, t0)
         if use_cache:
             fprint = 0
             if self.cheap_reads:
@@ -446,6 +457,81 @@ class _Pipeline(object):
             if ps is not None:
                 self.h2d_done[ps] = ev
             st.compute_stream.wait_event(ev)
+        if cacheable:
+            dims_c = None if dims is None else np.array(dims, copy=True)
+            st.cache[key] = (xyz_dev, dims_c, nbytes)
+            st.cache_used += nbytes
+        return xyz_dev, dims, time.time() - t0, slot
+
+    def _fetch_raw(self, frames, rb, use_cache, t0):
+        """frames as they lie in the file -> pinned ring -> device ->
+        rdfk_unpack_planes -> xyz [B,N,3]"""
+        st = self.st
+        raw, fstride, offs, dims = rb
+        B = raw.shape[0]
+        nbytes = B * self.frame_bytes
+        key = None
+        if use_cache:
+            flat = raw.reshape(-1)
+            step = max(1, flat.size // 16384)
+            sample = np.ascontiguousarray(flat[::step])
+            fprint = int(sample.astype(np.uint64).sum()) ^ (int(sample[::7].astype(np.uint64).sum()) << 20)
+            key = (self.traj_key, frames.start, frames.stop, frames.step,
+                   self.natoms, fprint)
+            hit = st.cache.get(key)
+            if hit is not None:
+                st.cache.move_to_end(key)
+                xyz_dev, dims_c, _ = hit
+                return xyz_dev, dims_c, time.time() - t0, None
+        cap = self.batch_frames * fstride
+        nraw = B * fstride
+        rs = self.rslot
+        self.rslot ^= 1
+        with torch.cuda.device(st.device):
+            for bufs, kw in ((st.raw_pin, {"pin_memory": True}),
+                             (st.raw_dev, {"device": st.device})):
+                if bufs[rs] is None or bufs[rs].numel() < cap:
+                    bufs[rs] = None
+                    bufs[rs] = torch.empty(cap, dtype=torch.uint8, **kw)
+            if self.h2d_raw_done[rs] is not None:
+                self.h2d_raw_done[rs].synchronize()     # pinned slot is free
+            _copy_frames(st.raw_pin[rs][:nraw].numpy().reshape(B, fstride), raw)
+            if self.raw_done[rs] is not None:           # device slot is free
+                st.copy_stream.wait_event(self.raw_done[rs])
+            with torch.cuda.stream(st.copy_stream):
+                st.raw_dev[rs][:nraw].copy_(st.raw_pin[rs][:nraw],
+                                            non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st.copy_stream)
+            self.h2d_raw_done[rs] = ev
+            st.compute_stream.wait_event(ev)
+            cacheable = use_cache and nbytes <= Config.cache_bytes
+            slot = None
+            if cacheable:
+                for k in [k for k in st.cache if k[:5] == key[:5]]:
+                    st.cache_used -= st.cache.pop(k)[2]
+                while st.cache and st.cache_used + nbytes > Config.cache_bytes:
+                    _, (_, _, freed) = st.cache.popitem(last=False)
+                    st.cache_used -= freed
+                xyz_dev = torch.empty((B, self.natoms, 3), dtype=torch.float32,
+                                      device=st.device)
+            else:
+                slot = self.dslot
+                self.dslot ^= 1
+                shape = (self.batch_frames, self.natoms, 3)
+                if st.staged[slot] is None or st.staged[slot].shape != shape:
+                    st.staged[slot] = None
+                    st.staged[slot] = torch.empty(shape, dtype=torch.float32,
+                                                  device=st.device)
+                xyz_dev = st.staged[slot][:B]
+            # the transpose runs on the compute stream, in order with the
+            # kernels that read (and last read) xyz_dev
+            _backend.unpack_planes(st.raw_dev[rs], fstride, offs[0], offs[1],
+                                   offs[2], B, self.natoms, xyz_dev,
+                                   st.compute_stream.cuda_stream)
+            evu = torch.cuda.Event()
+            evu.record(st.compute_stream)
+            self.raw_done[rs] = evu
         if cacheable:
             dims_c = None if dims is None else np.array(dims, copy=True)
             st.cache[key] = (xyz_dev, dims_c, nbytes)

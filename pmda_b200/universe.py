@@ -272,6 +272,12 @@ class Universe(object):
                    filename=positions_path)
 
     @classmethod
+    def from_dcd(cls, dcd_path, names=None):
+        """Universe over a memory-mapped DCD file (:mod:`pmda_b200.dcd`)"""
+        from .dcd import DCDTrajectory
+        return cls(DCDTrajectory(dcd_path), names=names, filename=dcd_path)
+
+    @classmethod
     def load(cls, path):
         z = np.load(path, allow_pickle=False)
         return cls(z["positions"],
