@@ -125,12 +125,12 @@ struct WsHeader {
   unsigned long long stats[4];  // slow pairs, all-slow frames, items, pairs
   int work_counter;
   float r2_cut[2];  // fp32 r2 >= r2_cut[t] => reference distance > r1 for sure
-  int pad[5];
+  int pad[5];       // pad[0]: triclinic refinement off (RDFK_DEBUG bit 2)
 };
 
 struct WsLayout {
   size_t header, extents, fparams, tables, g1, g2, s1, s2, gbb1, gbb2, cbb1,
-      cbb2, qbb1, qbb2, keys, lrank, cells, total;
+      cbb2, qbb1, qbb2, gbc1, gbc2, qbc1, qbc2, keys, lrank, cells, total;
   int np1, np2, bits1, bits2;
 };
 
@@ -180,6 +180,17 @@ static WsLayout ws_layout(int F, int n1, int n2, int nbins, int same_group) {
   w.qbb1 = off;
   off = align_up(off + sizeof(float) * 6 * (size_t)(w.np1 / 32) * (size_t)F, 256);
   w.qbb2 = same_group ? w.qbb1 : off;
+  if (!same_group)
+    off = align_up(off + sizeof(float) * 6 * (size_t)(w.np2 / 32) * (size_t)F, 256);
+  // Cartesian boxes of the groups / quarters (triclinic refinement test)
+  w.gbc1 = off;
+  off = align_up(off + sizeof(float) * 6 * (size_t)(w.np1 / GJ) * (size_t)F, 256);
+  w.gbc2 = same_group ? w.gbc1 : off;
+  if (!same_group)
+    off = align_up(off + sizeof(float) * 6 * (size_t)(w.np2 / GJ) * (size_t)F, 256);
+  w.qbc1 = off;
+  off = align_up(off + sizeof(float) * 6 * (size_t)(w.np1 / 32) * (size_t)F, 256);
+  w.qbc2 = same_group ? w.qbc1 : off;
   if (!same_group)
     off = align_up(off + sizeof(float) * 6 * (size_t)(w.np2 / 32) * (size_t)F, 256);
   // counting-sort scratch, shared by the two groups (used one after the other)
@@ -343,11 +354,13 @@ __device__ __forceinline__ FastBox load_fastbox(const FrameParams *fp) {
 // ---------------------------------------------------------------------------
 // init / stage / tables
 // ---------------------------------------------------------------------------
-__global__ void init_ws_kernel(WsHeader *h, int *extents, int F) {
+__global__ void init_ws_kernel(WsHeader *h, int *extents, int F,
+                               int no_refine) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0) {
     h->stats[0] = h->stats[1] = h->stats[2] = h->stats[3] = 0ull;
     h->work_counter = 0;
+    h->pad[0] = no_refine;
   }
   if (t < F * 6) extents[t] = (t % 6 < 3) ? INT_MAX : INT_MIN;
 }
@@ -850,7 +863,8 @@ template <int BOXKIND>
 __global__ __launch_bounds__(256) void bbox_kernel(
     const float *__restrict__ sorted, int np,
     const FrameParams *__restrict__ fparams, float *__restrict__ gbb,
-    float *__restrict__ qbb, float *__restrict__ cbb) {
+    float *__restrict__ qbb, float *__restrict__ cbb, float *__restrict__ gbc,
+    float *__restrict__ qbc) {
   const int f = blockIdx.y;
   const int ngrp = np / GJ, ncl = np / CI;   // ngrp is a multiple of GPC
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -860,6 +874,10 @@ __global__ __launch_bounds__(256) void bbox_kernel(
   const float *s = sorted + (size_t)f * 3 * np + (size_t)g * GJ;
   float lo[3] = {INFINITY, INFINITY, INFINITY};
   float hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  // triclinic cells: also the Cartesian box of the (wrapped) atoms, for the
+  // Euclidean refinement of the fractional max-norm bound
+  float clo[3] = {INFINITY, INFINITY, INFINITY};
+  float chi[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int u = 0; u < GJ; ++u) {
     const float x = s[u], y = s[(size_t)np + u], z = s[2 * (size_t)np + u];
@@ -871,6 +889,11 @@ __global__ __launch_bounds__(256) void bbox_kernel(
       for (int k = 0; k < 3; ++k) {
         lo[k] = fminf(lo[k], c[k]);
         hi[k] = fmaxf(hi[k], c[k]);
+      }
+      if (BOXKIND == RDFK_BOX_TRI) {
+        clo[0] = fminf(clo[0], x); chi[0] = fmaxf(chi[0], x);
+        clo[1] = fminf(clo[1], y); chi[1] = fmaxf(chi[1], y);
+        clo[2] = fminf(clo[2], z); chi[2] = fmaxf(chi[2], z);
       }
     }
   }
@@ -893,6 +916,7 @@ __global__ __launch_bounds__(256) void bbox_kernel(
     }
   };
   if (live) emit(gbb, ngrp, g, lo, hi);
+  if (BOXKIND == RDFK_BOX_TRI && live) emit(gbc, ngrp, g, clo, chi);
   // 4 groups -> one 32-atom quarter (the atoms one register index of the pair
   // kernel holds), 4 quarters -> the cluster
 #pragma unroll
@@ -901,8 +925,15 @@ __global__ __launch_bounds__(256) void bbox_kernel(
     for (int k = 0; k < 3; ++k) {
       lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
       hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      if (BOXKIND == RDFK_BOX_TRI && o <= 2) {
+        clo[k] = fminf(clo[k], __shfl_xor_sync(0xffffffffu, clo[k], o));
+        chi[k] = fmaxf(chi[k], __shfl_xor_sync(0xffffffffu, chi[k], o));
+      }
     }
-    if (o == 2 && live && (g & 3) == 0) emit(qbb, ngrp / 4, g / 4, lo, hi);
+    if (o == 2 && live && (g & 3) == 0) {
+      emit(qbb, ngrp / 4, g / 4, lo, hi);
+      if (BOXKIND == RDFK_BOX_TRI) emit(qbc, ngrp / 4, g / 4, clo, chi);
+    }
   }
   if (live && (g & (GPC - 1)) == 0) emit(cbb, ncl, g / GPC, lo, hi);
 }
@@ -914,6 +945,8 @@ struct PairArgs {
   const float *qbbi;  // quarter boxes of the i side [F][6][4 * ncl_i]
   const float *cbbj;  // cluster boxes of the j side [F][6][ncl_j]
   const float *gbbj;  // group boxes of the j side   [F][6][ngrp_j]
+  const float *qbci;  // triclinic: Cartesian quarter boxes of the i side
+  const float *gbcj;  // triclinic: Cartesian group boxes of the j side
   int np_i, np_j, F;
   int n_i, n_j;       // real atoms (the sorted arrays hold them first)
   int ncl_i, ncl_j, ngrp_j;
@@ -954,7 +987,8 @@ constexpr int SM_CODE = NSTAGE * 4;            // their (group, code, quarter ma
 constexpr int SM_LOG = LOGMAX * 4;             // group log (same words)
 constexpr int SM_MARK = LOGMAX * 32;           // queue marks (bytes)
 constexpr int SM_DUMMY = 32 * 4;               // per-lane sink for dead atomics
-constexpr int SM_QB = 24 * 4;                  // my 4 quarter boxes [6][4]
+constexpr int SM_QB = 2 * 24 * 4;              // my 4 quarter boxes [6][4], x2:
+                                               // prune space and Cartesian
 constexpr int SM_WARP =
     SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK + SM_DUMMY + SM_QB;
 constexpr int SM_FIXED = NWARP * SM_WARP;
@@ -1125,6 +1159,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   float2 *tab_s = reinterpret_cast<float2 *>(smem_raw + SM_FIXED + hist_bytes);
   const uint32_t tab_s32 = smem_u32(tab_s);
   const float cut0 = a.header->r2_cut[0], cut1 = a.header->r2_cut[1];
+  const bool refine = a.header->pad[0] == 0;
   // every copy has a dummy slot in front (index -1: "drop")
   const int hstride = nbins + 1;
   unsigned int *wh =
@@ -1181,9 +1216,12 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     __syncwarp();
     if (lane < 24) {
       const int k = lane >> 2, r = lane & 3;
-      qb[lane] = a.qbbi[((size_t)f * 6 + k) * (4 * (size_t)a.ncl_i) + 4 * ic + r];
+      const size_t at = ((size_t)f * 6 + k) * (4 * (size_t)a.ncl_i) + 4 * ic + r;
+      qb[lane] = a.qbbi[at];
+      if (BOXKIND == RDFK_BOX_TRI) qb[24 + lane] = a.qbci[at];
     }
     __syncwarp();
+    const float *gcj = a.gbcj + (size_t)f * 6 * a.ngrp_j;
 
     // lower bound of the distance between my cluster box and box (c, h) of
     // the j side, and the lattice shift code of the pair of boxes
@@ -1244,12 +1282,50 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
               wk[k]);
         }
         bool ok;
-        if (BOXKIND == RDFK_BOX_TRI)
+        if (BOXKIND == RDFK_BOX_TRI) {
           ok = fmaxf(gap[0], fmaxf(gap[1], gap[2])) <= rprune;
-        else
+          if (ok && refine) {
+            // Euclidean refinement.  The fractional bound holds for every
+            // lattice image; if along each lattice direction only the nearest
+            // image n_k can be in range ((1 - |D'| - h) w > rprune for the
+            // next one), the pair of boxes is in range only through the
+            // single image n, whose Cartesian box gap is tested here.
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            bool single = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float D = __fsub_rn(cj[k], qb[k * 4 + r]);
+              const float n = (D > 0.5f) ? 1.f : ((D < -0.5f) ? -1.f : 0.f);
+              const float Dn = fabsf(__fsub_rn(D, n));
+              const float hs = __fadd_rn(hj[k], qb[(3 + k) * 4 + r]);
+              single = single &&
+                       (__fmul_rn(__fsub_rn(__fsub_rn(1.f, Dn), hs), wk[k]) > rprune);
+              // n_k times lattice vector k (rows a, b, c of the box)
+              if (k == 0) { sx = __fmaf_rn(n, fb.ax, sx); }
+              if (k == 1) { sx = __fmaf_rn(n, fb.bx, sx); sy = __fmaf_rn(n, fb.by, sy); }
+              if (k == 2) { sx = __fmaf_rn(n, fb.cx, sx); sy = __fmaf_rn(n, fb.cy, sy);
+                            sz = __fmaf_rn(n, fb.cz, sz); }
+            }
+            if (single) {
+              const float sh[3] = {sx, sy, sz};
+              float e2 = 0.f;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const float Dc = __fsub_rn(
+                    __fsub_rn(gcj[(size_t)k * count + at], qb[24 + k * 4 + r]), sh[k]);
+                const float hc = __fadd_rn(gcj[(size_t)(3 + k) * count + at],
+                                           qb[24 + (3 + k) * 4 + r]);
+                const float ge = fmaxf(0.f, __fsub_rn(fabsf(Dc), hc));
+                e2 = __fmaf_rn(ge, ge, e2);
+              }
+              ok = e2 <= __fmul_rn(rprune, rprune);
+            }
+          }
+        } else {
           ok = __fmaf_rn(gap[2], gap[2],
                          __fmaf_rn(gap[1], gap[1], __fmul_rn(gap[0], gap[0]))) <=
                __fmul_rn(rprune, rprune);
+        }
         m |= ok ? (1 << r) : 0;
       }
       return m;
@@ -1846,7 +1922,8 @@ template <int BOXKIND>
 static int sort_side(const float *staged, int n, int np, int bits, int F,
                      const FrameParams *fparams, uint32_t *keys,
                      uint32_t *lrank, uint32_t *cells, float *sorted,
-                     float *gbb, float *qbb, float *cbb, cudaStream_t st) {
+                     float *gbb, float *qbb, float *cbb, float *gbc,
+                     float *qbc, cudaStream_t st) {
   const size_t ncell = (size_t)1 << (3 * bits);
   CUDA_TRY(cudaMemsetAsync(cells, 0, sizeof(uint32_t) * ncell * (size_t)F, st));
   key_kernel<BOXKIND><<<dim3((n + 255) / 256, F), 256, 0, st>>>(
@@ -1856,7 +1933,7 @@ static int sort_side(const float *staged, int n, int np, int bits, int F,
                                                         keys, lrank, cells,
                                                         sorted);
   bbox_kernel<BOXKIND><<<dim3((np / GJ + 255) / 256, F), 256, 0, st>>>(
-      sorted, np, fparams, gbb, qbb, cbb);
+      sorted, np, fparams, gbb, qbb, cbb, gbc, qbc);
   COUNT_LAUNCH(4);
   return RDFK_OK;
 }
@@ -1883,29 +1960,35 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   uint32_t *lrank = reinterpret_cast<uint32_t *>(ws + L.lrank);
   uint32_t *cells = reinterpret_cast<uint32_t *>(ws + L.cells);
 
-  init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(header, extents, F);
+  // RDFK_DEBUG: bit 0 = no pruning (every group is evaluated), bit 1 = no
+  // shifted variant, bit 2 = no Euclidean refinement of the triclinic box
+  // test.  Results must not depend on any of them (tests/).
+  int debug_flags = 0;
+  if (const char *dbg = getenv("RDFK_DEBUG")) debug_flags = atoi(dbg);
+  init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(
+      header, extents, F, (debug_flags & 4) ? 1 : 0);
   COUNT_LAUNCH(same_group ? 4 : 5);  // init + stage(s) + params + tables
   stage_kernel<BOXKIND><<<dim3((L.np1 + 255) / 256, F), 256, 0, st>>>(
       xyz, natoms, idx1, n1, L.np1, box, g1, extents);
   if (!same_group)
     stage_kernel<BOXKIND><<<dim3((L.np2 + 255) / 256, F), 256, 0, st>>>(
         xyz, natoms, idx2, n2, L.np2, box, g2, extents);
-  // RDFK_DEBUG: bit 0 = no pruning (every group is evaluated), bit 1 = no
-  // shifted variant.  Results must not depend on either (tests/).
-  int debug_flags = 0;
-  if (const char *dbg = getenv("RDFK_DEBUG")) debug_flags = atoi(dbg);
   params_kernel<<<(F + 127) / 128, 128, 0, st>>>(BOXKIND, box, extents, hp,
                                                  debug_flags, F, fparams);
   tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header);
 
   float *qbb1 = reinterpret_cast<float *>(ws + L.qbb1);
   float *qbb2 = reinterpret_cast<float *>(ws + L.qbb2);
+  float *gbc1 = reinterpret_cast<float *>(ws + L.gbc1);
+  float *gbc2 = reinterpret_cast<float *>(ws + L.gbc2);
+  float *qbc1 = reinterpret_cast<float *>(ws + L.qbc1);
+  float *qbc2 = reinterpret_cast<float *>(ws + L.qbc2);
   int rc = sort_side<BOXKIND>(g1, n1, L.np1, L.bits1, F, fparams, keys, lrank,
-                              cells, s1, gbb1, qbb1, cbb1, st);
+                              cells, s1, gbb1, qbb1, cbb1, gbc1, qbc1, st);
   if (rc) return rc;
   if (!same_group) {
     rc = sort_side<BOXKIND>(g2, n2, L.np2, L.bits2, F, fparams, keys, lrank,
-                            cells, s2, gbb2, qbb2, cbb2, st);
+                            cells, s2, gbb2, qbb2, cbb2, gbc2, qbc2, st);
     if (rc) return rc;
   }
 
@@ -1918,6 +2001,8 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   a.qbbi = swap ? qbb2 : qbb1;
   a.cbbj = swap ? cbb1 : cbb2;
   a.gbbj = swap ? gbb1 : gbb2;
+  a.qbci = swap ? qbc2 : qbc1;
+  a.gbcj = swap ? gbc1 : gbc2;
   a.np_i = swap ? L.np2 : L.np1;
   a.np_j = swap ? L.np1 : L.np2;
   a.n_i = swap ? n2 : n1;
