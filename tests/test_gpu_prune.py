@@ -207,3 +207,25 @@ def test_lattice_on_edges_all_modes():
     u = Universe(pos, [L, L, L, 90, 90, 90])
     _check_all_modes(u, u.atoms, u.atoms, nbins=20, rng=(0.0, 6.0))
     _check_all_modes(u, u.atoms, u.atoms, nbins=30, rng=(0.0, 9.0))
+
+
+def test_large_coordinate_offsets_and_anisotropic_boxes():
+    """error bounds scale with the coordinate magnitude: far from the origin
+    many more pairs take the fp64 path, the integers stay the oracle's"""
+    rng = np.random.default_rng(116)
+    L = np.array([40.0, 40.0, 40.0])
+    pos = (rng.random((2, 3000, 3)) * L + np.array([5000.0, -7000.0, 12000.0])
+           ).astype(np.float32)
+    u = Universe(pos, list(L) + [90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 12.0))
+    # a slab-like cell: one axis barely longer than twice the cut-off
+    L = np.array([200.0, 31.0, 25.0])
+    pos = (rng.random((2, 4000, 3)) * L).astype(np.float32)
+    u = Universe(pos, list(L) + [90, 90, 90])
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 12.0))
+    _check_all_modes(u, u.atoms[:900], u.atoms[900:], nbins=30, rng=(3.0, 12.4))
+    # flat triclinic cell with a large offset along one lattice direction
+    dims = [90.0, 35.0, 30.0, 70.0, 95.0, 100.0]
+    pos = synthetic.uniform_triclinic(2, 4000, dims, rng)
+    u = Universe(pos, dims)
+    _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 11.0))
