@@ -48,6 +48,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "rdfk.h"
 
 // ---------------------------------------------------------------------------
@@ -1270,7 +1272,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         hj[k] = bb[(size_t)(3 + k) * count + at];
       }
       int m = 0;
-#pragma unroll
+#pragma unroll 1   // one copy of the test: code size (i-cache) matters here
       for (int r = 0; r < RI; ++r) {
         float gap[3];
 #pragma unroll
@@ -1358,21 +1360,22 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     // MUFU.SQRT and a magic-number round (no F2I), the tables have a "drop"
     // entry in front, inactive / failed slots go to a per-lane dummy word,
     // band failures are collected in a mask and resolved after the loop.
-    auto drain = [&]() {
+    auto drain_w = [&](auto width_tag) {
+      constexpr int DWL = decltype(width_tag)::value;
       __syncwarp();   // the group log was written by lane 0
       const int n = (int)((qaddr - qbase) >> 7);
       const int nmax = __reduce_max_sync(0xffffffffu, n);
       const float inv_dr = fp->inv_dr, koffm = fp->koffm;
       const unsigned int toff = cls ? (unsigned int)nb1 + 1u : 1u;
       unsigned long long failmask = 0ull;   // bit s: entry s needs the fp64 path
-      for (int s = 0; s < nmax; s += DW) {
-        float v[DW];
+      for (int s = 0; s < nmax; s += DWL) {
+        float v[DWL];
 #pragma unroll
-        for (int u = 0; u < DW; ++u) v[u] = q[(s + u) * 32 + lane];
+        for (int u = 0; u < DWL; ++u) v[u] = q[(s + u) * 32 + lane];
         unsigned int okmask = 0u;
         const int rem = n - s;   // entries s .. s + rem - 1 are live
 #pragma unroll
-        for (int u = 0; u < DW; ++u) {
+        for (int u = 0; u < DWL; ++u) {
           const float r2 = v[u];
           // floor(sqrt * inv_dr + koff) as round-to-nearest of (.. - 0.5),
           // read out of the mantissa of (.. + 1.5 * 2^23)
@@ -1406,7 +1409,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         }
         // live entries that were not certain need the fp64 path
         const unsigned int livemask =
-            rem >= DW ? (unsigned int)((1ull << DW) - 1ull)
+            rem >= DWL ? (unsigned int)((1ull << DWL) - 1ull)
                       : ((1u << (rem > 0 ? rem : 0)) - 1u);
         const unsigned int fail = livemask & ~okmask;
         failmask |= (unsigned long long)fail << s;
@@ -1433,6 +1436,12 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       added += 64u * (unsigned int)nmax;
       maybe_flush();
     };
+    // the full-width instance is inlined once, in evaluate(); the drains at
+    // the end of a phase (a few per work item, short queues) use a narrow one:
+    // three unrolled copies of the wide loop overflowed the instruction cache
+    // of the triclinic instantiation (ncu: no_instruction 3.6 per issue)
+    auto drain = [&]() { drain_w(std::integral_constant<int, DW>()); };
+    auto drain_small = [&]() { drain_w(std::integral_constant<int, 2>()); };
 
     // evaluate staged j-group `slot` against my RI i-atoms
     auto evaluate = [&](int slot) {
@@ -1575,7 +1584,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
             cv = lane == 0;
           } else {
             if (rr == 1) {   // leaving my own cluster: the weight changes
-              if (!all_slow) drain();
+              if (!all_slow) drain_small();
               weight = 2u;
             }
             const int t = (rr - 1) * 32 + lane;
@@ -1632,7 +1641,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
           for (int h = 0; h < nh; ++h) evaluate(h);
         }
       }
-      if (!all_slow) drain();
+      if (!all_slow) drain_small();
     }
   }
 
