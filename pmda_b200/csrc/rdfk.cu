@@ -991,8 +991,9 @@ constexpr int SM_MARK = LOGMAX * 32;           // queue marks (bytes)
 constexpr int SM_DUMMY = 32 * 4;               // per-lane sink for dead atomics
 constexpr int SM_QB = 2 * 24 * 4;              // my 4 quarter boxes [6][4], x2:
                                                // prune space and Cartesian
+constexpr int SM_CTX = 32 * 4;                 // per-item constants of the box tests
 constexpr int SM_WARP =
-    SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK + SM_DUMMY + SM_QB;
+    SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK + SM_DUMMY + SM_QB + SM_CTX;
 constexpr int SM_FIXED = NWARP * SM_WARP;
 
 // hit <=> r2 < cut
@@ -1150,6 +1151,11 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       smem_u32(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK) + 4u * lane;
   float *qb = reinterpret_cast<float *>(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG +
                                         SM_MARK + SM_DUMMY);   // [6][4]
+  // per-item constants that only the box tests read (cluster box, periods, gap
+  // scales, lattice vectors) live in shared memory, not in registers: the
+  // triclinic instantiation spilled in its hot loops
+  float *ctx = reinterpret_cast<float *>(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG +
+                                         SM_MARK + SM_DUMMY + SM_QB);
   unsigned int *hist_s = reinterpret_cast<unsigned int *>(smem_raw + SM_FIXED);
 
   const int nbins = a.hp.nbins;
@@ -1191,7 +1197,6 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     ++n_items;
     const int f = item / a.ncl_i, ic = item - f * a.ncl_i;
     const FrameParams *fp = a.fparams + f;
-    const FastBox fb = load_fastbox(fp);
     const int all_slow = fp->all_slow;
     const int shift_ok = fp->shift_ok;
     const size_t np_i = (size_t)a.np_i, np_j = (size_t)a.np_j;
@@ -1200,19 +1205,25 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     const float *cbj = a.cbbj + (size_t)f * 6 * a.ncl_j;
     const float *gbj = a.gbbj + (size_t)f * 6 * a.ngrp_j;
 
-    // my cluster's box (prune space)
-    float cc[3], ch[3];
-    {
+    // ctx: [0..2] cluster centre, [3..5] half-width (prune space), [6..8]
+    // period, [9..11] gap scale, [12] rprune, [13] rshift, [14..19] lattice
+    // ax bx by cx cy cz
+    __syncwarp();
+    if (lane < 20) {
       const float *cb = a.cbbi + (size_t)f * 6 * a.ncl_i;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        cc[k] = cb[(size_t)k * a.ncl_i + ic];
-        ch[k] = cb[(size_t)(3 + k) * a.ncl_i + ic];
+      float v;
+      if (lane < 6) v = cb[(size_t)lane * a.ncl_i + ic];
+      else if (lane < 9) v = fp->per[lane - 6];
+      else if (lane < 12) v = fp->wk[lane - 9];
+      else if (lane == 12) v = fp->rprune;
+      else if (lane == 13) v = fp->rshift;
+      else {
+        const int t = lane - 14;   // tri[0], [3], [4], [6], [7], [8]
+        v = fp->tri[t == 0 ? 0 : (t == 1 ? 3 : (t == 2 ? 4 : t + 3))];
       }
+      ctx[lane] = v;
     }
-    const float per[3] = {fp->per[0], fp->per[1], fp->per[2]};
-    const float wk[3] = {fp->wk[0], fp->wk[1], fp->wk[2]};
-    const float rprune = fp->rprune, rshift = fp->rshift;
+    const float rprune = fp->rprune;
 
     // my four quarter boxes -> shared memory [6][4]
     __syncwarp();
@@ -1234,22 +1245,23 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const float cj = bb[(size_t)k * count + at];
-        const float hs = __fadd_rn(ch[k], bb[(size_t)(3 + k) * count + at]);
-        const float D = __fsub_rn(cj, cc[k]);
+        const float hs = __fadd_rn(ctx[3 + k], bb[(size_t)(3 + k) * count + at]);
+        const float D = __fsub_rn(cj, ctx[k]);
         float d = fabsf(D);
-        d = fminf(d, __fsub_rn(per[k], d));
-        gap[k] = __fmul_rn(fmaxf(0.f, __fsub_rn(d, hs)), wk[k]);
+        const float perk = ctx[6 + k], wkk = ctx[9 + k];
+        d = fminf(d, __fsub_rn(perk, d));
+        gap[k] = __fmul_rn(fmaxf(0.f, __fsub_rn(d, hs)), wkk);
         if (BOXKIND != RDFK_BOX_NONE) {
           // lattice shift of this pair of boxes along k, and whether it is
           // the only image of any of their pairs that can be in range:
           // every other image is at least (per - |D'| - hs) * wk away
-          const float hp_ = __fmul_rn(0.5f, per[k]);
+          const float hp_ = __fmul_rn(0.5f, perk);
           const int n = (D > hp_) ? 1 : ((D < -hp_) ? -1 : 0);
-          const float Dn = fabsf(__fsub_rn(D, __fmul_rn((float)n, per[k])));
-          if (per[k] < INFINITY) {
+          const float Dn = fabsf(__fsub_rn(D, __fmul_rn((float)n, perk)));
+          if (perk < INFINITY) {
             valid = valid &&
-                    (__fmaf_rn(__fadd_rn(Dn, hs), wk[k], rshift) <
-                     __fmul_rn(per[k], wk[k]));
+                    (__fmaf_rn(__fadd_rn(Dn, hs), wkk, ctx[13]) <
+                     __fmul_rn(perk, wkk));
             code += n * (1 << (2 * k));
           }
         }
@@ -1278,10 +1290,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           float d = fabsf(__fsub_rn(cj[k], qb[k * 4 + r]));
-          d = fminf(d, __fsub_rn(per[k], d));
+          d = fminf(d, __fsub_rn(ctx[6 + k], d));
           gap[k] = __fmul_rn(
               fmaxf(0.f, __fsub_rn(d, __fadd_rn(hj[k], qb[(3 + k) * 4 + r]))),
-              wk[k]);
+              ctx[9 + k]);
         }
         bool ok;
         if (BOXKIND == RDFK_BOX_TRI) {
@@ -1301,12 +1313,12 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
               const float Dn = fabsf(__fsub_rn(D, n));
               const float hs = __fadd_rn(hj[k], qb[(3 + k) * 4 + r]);
               single = single &&
-                       (__fmul_rn(__fsub_rn(__fsub_rn(1.f, Dn), hs), wk[k]) > rprune);
+                       (__fmul_rn(__fsub_rn(__fsub_rn(1.f, Dn), hs), ctx[9 + k]) > rprune);
               // n_k times lattice vector k (rows a, b, c of the box)
-              if (k == 0) { sx = __fmaf_rn(n, fb.ax, sx); }
-              if (k == 1) { sx = __fmaf_rn(n, fb.bx, sx); sy = __fmaf_rn(n, fb.by, sy); }
-              if (k == 2) { sx = __fmaf_rn(n, fb.cx, sx); sy = __fmaf_rn(n, fb.cy, sy);
-                            sz = __fmaf_rn(n, fb.cz, sz); }
+              if (k == 0) { sx = __fmaf_rn(n, ctx[14], sx); }
+              if (k == 1) { sx = __fmaf_rn(n, ctx[15], sx); sy = __fmaf_rn(n, ctx[16], sy); }
+              if (k == 2) { sx = __fmaf_rn(n, ctx[17], sx); sy = __fmaf_rn(n, ctx[18], sy);
+                            sz = __fmaf_rn(n, ctx[19], sz); }
             }
             if (single) {
               const float sh[3] = {sx, sy, sz};
@@ -1485,8 +1497,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       ++nlog;
       if (code != cur_code) {
         float sx = 0.f, sy = 0.f, sz = 0.f;
-        if (BOXKIND != RDFK_BOX_NONE && (code & CODE_PLAIN))
-          decode_shift<BOXKIND>(code, fb, sx, sy, sz);
+        if (BOXKIND != RDFK_BOX_NONE && (code & CODE_PLAIN)) {
+          const FastBox fbs = load_fastbox(fp);
+          decode_shift<BOXKIND>(code, fbs, sx, sy, sz);
+        }
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
           nxs[r] = -__fadd_rn(gi_cl[r * 32 + lane], sx);
@@ -1530,6 +1544,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         }
       } else {
         // per-pair minimum image (ortho rint / triclinic brick), same order
+        const FastBox fb = load_fastbox(fp);
         const float4 Xa = *reinterpret_cast<const float4 *>(js);
         const float4 Xb = *reinterpret_cast<const float4 *>(js + 4);
         const float4 Ya = *reinterpret_cast<const float4 *>(js + GJ);
