@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RDFK_VERSION 110
+#define RDFK_VERSION 120
 
 #define RDFK_OK 0
 #define RDFK_EINVAL -1    /* bad argument                                   */
@@ -148,6 +148,45 @@ int rdfk_contacts(const float *xyz, int F, int natoms, const int *idx_a,
 int rdfk_unpack_planes(const void *raw, long long frame_stride,
                        long long off_x, long long off_y, long long off_z,
                        int F, int natoms, float *xyz, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Hydrogen-bond search.  Replaces, for F frames at
+ * once, the body of pmda/hbond_analysis.py:415-470
+ * (HydrogenBondAnalysis._single_frame):
+ *   pairs, d = capped_distance(donors.positions, acceptors.positions,
+ *                              max_cutoff, min_cutoff=1.0, box, True)
+ *   ang = rad2deg(calc_angles(D[pairs[:,0]], H[pairs[:,0]], A[pairs[:,1]], box))
+ *   keep = ang > angle_cutoff_deg
+ * The result is ragged; it is written compacted, ordered by (frame, D-H row,
+ * acceptor) -- the row-major order of the reference's brute-force search.
+ *
+ *   donors/hydrogens [n_dh] int32  paired atom indices (row k = donor k with
+ *                                  its hydrogen k; a donor with two hydrogens
+ *                                  appears twice)
+ *   hydrogens == NULL              plain capped_distance(donors, acceptors):
+ *                                  no angle, out_angle may be NULL
+ *                                  (pmda/hbond_analysis.py:372-378 uses this
+ *                                  to pair donors with hydrogens)
+ *   acceptors [n_acc] int32
+ *   min_cutoff < 0                 no lower bound (the reference's None)
+ *   capacity                       rows the out_* arrays can hold
+ *   out_row  [capacity] int32      frame * n_dh + k
+ *   out_acc  [capacity] int32      position in `acceptors`
+ *   out_dist [capacity] float64    D..A distance, the reference's bits
+ *   out_angle[capacity] float64    D-H..A angle in degrees
+ *   total    device int64          number of rows found.  When it exceeds
+ *                                  `capacity` only the first `capacity` rows
+ *                                  were written: call again with larger arrays.
+ * ------------------------------------------------------------------------ */
+size_t rdfk_hbonds_workspace_bytes(int F, int n_dh, int n_acc);
+
+int rdfk_hbonds(const float *xyz, int F, int natoms, const int *donors,
+                const int *hydrogens, int n_dh, const int *acceptors,
+                int n_acc, int boxkind, const float *box, double max_cutoff,
+                double min_cutoff, double angle_cutoff_deg, long long capacity,
+                int *out_row, int *out_acc, double *out_dist,
+                double *out_angle, long long *total, void *workspace,
+                size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
  * Diagnostics / measurement helpers (not on the reference path).

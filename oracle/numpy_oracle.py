@@ -65,6 +65,8 @@ def check_box(box):
     """-> ('none', None) | ('ortho', float32[3]) | ('tri_vecs', float32[3,3])"""
     if box is None:
         return "none", None
+    if isinstance(box, tuple):      # already classified (tests/fake_backend.py)
+        return box
     box = np.asarray(box, dtype=np.float32, order="C")
     if box.shape != (6,):
         raise ValueError("Invalid box information. Must be of the form "
@@ -119,6 +121,17 @@ def distance_array(ref, conf, box=None):
         conf = _wrap_triclinic(conf, b)
     # FLOAT32 subtraction conf[j] - ref[i], then widened to double
     dx = (conf[None, :, :] - ref[:, None, :]).astype(np.float64)
+    dx = _minimum_image(dx, kind, b)
+    rsq = (dx[..., 0] * dx[..., 0]) + (dx[..., 1] * dx[..., 1]) \
+        + (dx[..., 2] * dx[..., 2])
+    return np.sqrt(rsq)
+
+
+def _minimum_image(dx, kind, b):
+    """minimum_image / minimum_image_triclinic (calc_distances.h) applied to
+    float64 difference vectors dx[..., 3] of (already wrapped, if triclinic)
+    float32 coordinates."""
+    dx = np.array(dx, dtype=np.float64)
     if kind == "ortho":
         inv = (1.0 / b.astype(np.float64)).astype(np.float32)
         for k in range(3):
@@ -127,7 +140,7 @@ def distance_array(ref, conf, box=None):
                 dx[..., k] = np.float64(b[k]) * (s - _round_half_away(s))
     elif kind == "tri_vecs":
         bf = b.ravel()  # float32; box[k]*i is a float product (exact for +-1)
-        best = np.full(dx.shape[:2], FLT_MAX, dtype=np.float64)
+        best = np.full(dx.shape[:-1], FLT_MAX, dtype=np.float64)
         best_v = np.zeros_like(dx)
         for ix in (-1, 0, 1):
             rx = dx[..., 0] + np.float64(bf[0] * np.float32(ix))
@@ -145,9 +158,7 @@ def distance_array(ref, conf, box=None):
                     best_v[..., 1] = np.where(upd, rz1, best_v[..., 1])
                     best_v[..., 2] = np.where(upd, rz2, best_v[..., 2])
         dx = best_v
-    rsq = (dx[..., 0] * dx[..., 0]) + (dx[..., 1] * dx[..., 1]) \
-        + (dx[..., 2] * dx[..., 2])
-    return np.sqrt(rsq)
+    return dx
 
 
 def capped_distance(ref, conf, max_cutoff, box=None):
@@ -210,3 +221,89 @@ def contacts_single_frame(frame_no, posA, posB, initial_contacts, r0s,
     if len(y) == 1:
         y = y[0]
     return y
+
+
+# ---------------------------------------------------------------------------
+# HydrogenBondAnalysis (pmda/hbond_analysis.py:415-470).  TEST INFRASTRUCTURE.
+# ---------------------------------------------------------------------------
+def capped_distance_minmax(ref, conf, max_cutoff, min_cutoff=None, box=None,
+                           distance_fn=None):
+    """capped_distance(..., min_cutoff=...) through _bruteforce_capped
+    [recalled-upstream lib/distances.py]: ``d <= max_cutoff`` then
+    ``d > min_cutoff``; pairs in the row-major order of np.where."""
+    fn = distance_array if distance_fn is None else distance_fn
+    d = fn(ref, conf, box=box)
+    keep = d <= max_cutoff
+    if min_cutoff is not None:
+        keep &= d > min_cutoff
+    mask = np.where(keep)
+    pairs = np.c_[mask[0], mask[1]].astype(np.intp)
+    return pairs, d[mask]
+
+
+def calc_angles(a, b, c, box=None):
+    """MDAnalysis.lib.distances.calc_angles -> radians float64 [n]: angle at
+    the apex b between b->a and b->c.  C loops of calc_distances.h
+    (_calc_angle / _calc_angle_ortho / _calc_angle_triclinic)
+    [recalled-upstream]: rji = a - b and rjk = c - b are FLOAT32 differences
+    widened to double, minimum-imaged like a distance vector (triclinic: of the
+    wrapped coordinates), then atan2(|rji x rjk|, rji . rjk)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    c = np.ascontiguousarray(c, dtype=np.float32)
+    kind, bx = check_box(box)
+    if kind == "tri_vecs":
+        a, b, c = (_wrap_triclinic(v, bx) for v in (a, b, c))
+    rji = _minimum_image((a - b).astype(np.float64), kind, bx)
+    rjk = _minimum_image((c - b).astype(np.float64), kind, bx)
+    x = (rji[:, 0] * rjk[:, 0] + rji[:, 1] * rjk[:, 1]) + rji[:, 2] * rjk[:, 2]
+    xp0 = rji[:, 1] * rjk[:, 2] - rji[:, 2] * rjk[:, 1]
+    xp1 = -rji[:, 0] * rjk[:, 2] + rji[:, 2] * rjk[:, 0]
+    xp2 = rji[:, 0] * rjk[:, 1] - rji[:, 1] * rjk[:, 0]
+    y = np.sqrt((xp0 * xp0 + xp1 * xp1) + xp2 * xp2)
+    return np.arctan2(y, x)
+
+
+def hbond_rows(positions, donors, hydrogens, acceptors, dimensions,
+               max_cutoff, min_cutoff, d_h_a_angle, distance_fn=None):
+    """the search of HydrogenBondAnalysis._single_frame
+    (pmda/hbond_analysis.py:427-452) -> (k, j, dist, angle_deg): row k of the
+    paired donor / hydrogen lists bonded to acceptor j (positions in the
+    lists), in the reference's order.  `hydrogens` None: capped_distance only
+    (angle 0)."""
+    positions = np.asarray(positions, dtype=np.float32)
+    donors = np.asarray(donors, dtype=np.intp)
+    acceptors = np.asarray(acceptors, dtype=np.intp)
+    pairs, dist = capped_distance_minmax(
+        positions[donors], positions[acceptors], max_cutoff, min_cutoff,
+        box=dimensions, distance_fn=distance_fn)
+    k, j = pairs[:, 0], pairs[:, 1]
+    if hydrogens is None:
+        return k, j, dist, np.zeros(len(k))
+    hydrogens = np.asarray(hydrogens, dtype=np.intp)
+    ang = np.rad2deg(calc_angles(positions[donors[k]], positions[hydrogens[k]],
+                                 positions[acceptors[j]], box=dimensions))
+    keep = np.where(ang > d_h_a_angle)[0]
+    return k[keep], j[keep], dist[keep], ang[keep]
+
+
+def hbonds_single_frame(frame_no, positions, donors, hydrogens, acceptors,
+                        dimensions, d_a_cutoff=3.0, d_h_a_angle=150.0,
+                        min_cutoff=1.0, distance_fn=None):
+    """HydrogenBondAnalysis._single_frame restated
+    (pmda/hbond_analysis.py:415-470) -> float64 [n_hbonds, 6]:
+    frame, donor index, hydrogen index, acceptor index, distance, angle.
+    `donors` / `hydrogens` are the paired index lists of _get_dh_pairs."""
+    donors, hydrogens, acceptors = (np.asarray(v, dtype=np.intp)
+                                    for v in (donors, hydrogens, acceptors))
+    k, j, dist, ang = hbond_rows(positions, donors, hydrogens, acceptors,
+                                 dimensions, d_a_cutoff, min_cutoff,
+                                 d_h_a_angle, distance_fn)
+    out = np.empty((len(k), 6), dtype=np.float64)
+    out[:, 0] = frame_no
+    out[:, 1] = donors[k]
+    out[:, 2] = hydrogens[k]
+    out[:, 3] = acceptors[j]
+    out[:, 4] = dist
+    out[:, 5] = ang
+    return out

@@ -49,6 +49,13 @@ def _declare(L):
     L.rdfk_unpack_planes.restype = c_int
     L.rdfk_unpack_planes.argtypes = [c_void_p, c_ll, c_ll, c_ll, c_ll, c_int,
                                      c_int, c_void_p, c_void_p]
+    L.rdfk_hbonds_workspace_bytes.restype = c_size_t
+    L.rdfk_hbonds_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.rdfk_hbonds.restype = c_int
+    L.rdfk_hbonds.argtypes = [
+        c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+        c_int, c_void_p, c_double, c_double, c_double, c_ll, c_void_p,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.rdfk_rdf_stats.restype = c_int
     L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
                                  c_void_p]
@@ -62,6 +69,7 @@ def _declare(L):
 EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
            "rdfk_contacts", "rdfk_unpack_planes",
+           "rdfk_hbonds_workspace_bytes", "rdfk_hbonds",
            "rdfk_rdf_stats", "rdfk_launch_count", "rdfk_measure_fp32_peak")
 
 
@@ -152,6 +160,25 @@ def unpack_planes(raw, frame_stride, off_x, off_y, off_z, F, natoms, xyz,
     check(lib().rdfk_unpack_planes(
         _ptr(raw), int(frame_stride), int(off_x), int(off_y), int(off_z),
         int(F), int(natoms), _ptr(xyz), ctypes.c_void_p(int(stream))))
+
+
+def hbonds_workspace_bytes(F, n_dh, n_acc):
+    return int(lib().rdfk_hbonds_workspace_bytes(int(F), int(n_dh), int(n_acc)))
+
+
+def hbonds(xyz, F, natoms, donors, hydrogens, n_dh, acceptors, n_acc, boxkind,
+           box, max_cutoff, min_cutoff, angle_cutoff, capacity, out_row,
+           out_acc, out_dist, out_angle, total, workspace, stream):
+    """rdfk_hbonds: `hydrogens` None = plain capped_distance; `min_cutoff`
+    None = no lower bound; `total` is a one-element int64 device tensor."""
+    check(lib().rdfk_hbonds(
+        _ptr(xyz), int(F), int(natoms), _ptr(donors), _ptr(hydrogens),
+        int(n_dh), _ptr(acceptors), int(n_acc), int(boxkind), _ptr(box),
+        float(max_cutoff), -1.0 if min_cutoff is None else float(min_cutoff),
+        float(angle_cutoff), int(capacity), _ptr(out_row), _ptr(out_acc),
+        _ptr(out_dist), _ptr(out_angle), _ptr(total), _ptr(workspace),
+        int(workspace.numel() * workspace.element_size()),
+        ctypes.c_void_p(int(stream))))
 
 
 def rdf_stats(workspace, stream):

@@ -35,7 +35,8 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = SOURCES + [os.path.join(INCLUDE, "rdfk.h"), os.path.abspath(__file__)]
+    deps = SOURCES + [os.path.join(HERE, "hbond.cuh"),
+                      os.path.join(INCLUDE, "rdfk.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -1,0 +1,424 @@
+// hbond.cuh -- donor..acceptor search + D-H..A angle filter with a ragged
+// (compacted) result: the hot path of pmda.hbond_analysis.HydrogenBondAnalysis
+// (pmda/hbond_analysis.py:415-470) and, without hydrogens, a stand-alone
+// MDAnalysis.lib.distances.capped_distance(ref, conf, max_cutoff, min_cutoff,
+// box).  Included at the end of rdfk.cu (one translation unit: it reuses
+// stage_kernel / params_kernel / tables_kernel and their error bounds).
+//
+// Per call (F frames):
+//   stage donors, hydrogens, acceptors (gather, AoS -> SoA, triclinic wrap)
+//   params + tables          -> r2_cut: fp32 r2 >= r2_cut  =>  reference d > cut
+//   hb_kernel<.., false>     count the hydrogen bonds of every (frame, D-H row)
+//   hb_scan_kernel           exclusive scan of the per-CTA totals (+ grand total)
+//   hb_kernel<.., true>      same search again, rows written at their offsets
+// The result is ordered by (frame, D-H row, acceptor): the row-major order of
+// the reference's brute-force `np.where(mask)`.
+//
+// Arithmetic: every pair is screened with the fp32 per-pair minimum image of
+// the RDF kernel; survivors (a fraction of a percent) are decided in fp64 with
+// the reference's operation order -- d <= max_cutoff, d > min_cutoff, and
+// rad2deg(atan2(|rji x rjk|, rji . rjk)) > angle_cutoff -- so the pair set and
+// the distances are the oracle's bit for bit; angles go through CUDA's atan2
+// (<= 2 ulp from glibc's).
+
+struct HbLayout {
+  size_t header, extents, fparams, tables, edges, gd, gh, ga, rowcount, blocksum,
+      total;
+  int npd, npa, nblk_x;
+};
+
+static HbLayout hb_layout(int F, int n_dh, int n_acc) {
+  HbLayout w;
+  w.npd = (int)align_up((size_t)(n_dh > 0 ? n_dh : 1), TILE);
+  w.npa = (int)align_up((size_t)(n_acc > 0 ? n_acc : 1), TILE);
+  w.nblk_x = (n_dh + 255) / 256;
+  size_t off = 0;
+  w.header = off;
+  off = align_up(off + sizeof(WsHeader), 256);
+  w.extents = off;
+  off = align_up(off + sizeof(int) * 6 * (size_t)F, 256);
+  w.fparams = off;
+  off = align_up(off + sizeof(FrameParams) * (size_t)F, 256);
+  w.tables = off;
+  off = align_up(off + sizeof(float2) * 2 * 2, 256);
+  w.edges = off;
+  off = align_up(off + sizeof(double) * 2, 256);
+  w.gd = off;
+  off = align_up(off + sizeof(float) * 3 * (size_t)w.npd * (size_t)F, 256);
+  w.gh = off;
+  off = align_up(off + sizeof(float) * 3 * (size_t)w.npd * (size_t)F, 256);
+  w.ga = off;
+  off = align_up(off + sizeof(float) * 3 * (size_t)w.npa * (size_t)F, 256);
+  w.rowcount = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)w.nblk_x * 256 * (size_t)F, 256);
+  w.blocksum = off;
+  off = align_up(off + sizeof(long long) * ((size_t)w.nblk_x * (size_t)F + 1), 256);
+  w.total = off;
+  return w;
+}
+
+// minimum-image vector r_j - r_i with the reference's arithmetic (see
+// exact_bin): float difference widened to double, then minimum_image /
+// minimum_image_triclinic.  Triclinic inputs are the wrapped coordinates.
+template <int BOXKIND>
+__device__ __forceinline__ void exact_vec(float xi, float yi, float zi, float xj,
+                                          float yj, float zj,
+                                          const FrameParams *__restrict__ fp,
+                                          double v[3]) {
+  v[0] = (double)__fsub_rn(xj, xi);
+  v[1] = (double)__fsub_rn(yj, yi);
+  v[2] = (double)__fsub_rn(zj, zi);
+  if (BOXKIND == RDFK_BOX_ORTHO) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float L = fp->L[k];
+      if (L > FLT_EPSILON) {
+        const double s = __dmul_rn((double)fp->inv[k], v[k]);
+        v[k] = __dmul_rn((double)L, __dsub_rn(s, round(s)));
+      }
+    }
+  } else if (BOXKIND == RDFK_BOX_TRI) {
+    const float *b = fp->tri;
+    double mn0 = 0.0, mn1 = 0.0, mn2 = 0.0;
+    double dsq_min = (double)FLT_MAX;
+    for (int ix = -1; ix < 2; ++ix) {
+      const double rx = __dadd_rn(v[0], (double)__fmul_rn(b[0], (float)ix));
+      for (int iy = -1; iy < 2; ++iy) {
+        const double ry0 = __dadd_rn(rx, (double)__fmul_rn(b[3], (float)iy));
+        const double ry1 = __dadd_rn(v[1], (double)__fmul_rn(b[4], (float)iy));
+        for (int iz = -1; iz < 2; ++iz) {
+          const double rz0 = __dadd_rn(ry0, (double)__fmul_rn(b[6], (float)iz));
+          const double rz1 = __dadd_rn(ry1, (double)__fmul_rn(b[7], (float)iz));
+          const double rz2 = __dadd_rn(v[2], (double)__fmul_rn(b[8], (float)iz));
+          const double dsq =
+              __dadd_rn(__dadd_rn(__dmul_rn(rz0, rz0), __dmul_rn(rz1, rz1)),
+                        __dmul_rn(rz2, rz2));
+          if (dsq < dsq_min) {
+            dsq_min = dsq;
+            mn0 = rz0; mn1 = rz1; mn2 = rz2;
+          }
+        }
+      }
+    }
+    v[0] = mn0; v[1] = mn1; v[2] = mn2;
+  }
+}
+
+struct HbArgs {
+  const float *gd, *gh, *ga;  // staged donors / hydrogens / acceptors (SoA)
+  int npd, npa, n_dh, n_acc;
+  const FrameParams *fparams;
+  const WsHeader *header;
+  double max_cutoff, min_cutoff, angle_cutoff;  // min_cutoff < 0: none
+  int has_h;
+  uint32_t *rowcount;     // [F][nblk_x * 256]
+  long long *blocksum;    // [F * nblk_x + 1]: totals, then exclusive offsets
+  long long capacity;
+  int *out_row, *out_acc;
+  double *out_dist, *out_angle;
+};
+
+constexpr int HB_TJ = 1024;  // acceptors staged in shared memory per round
+
+// One candidate of the fp32 screen, decided with the reference arithmetic.
+// Returns true for a hydrogen bond (or a capped pair when there is no
+// hydrogen); *d_out / *ang_out are the reference's float64 results.
+template <int BOXKIND>
+__device__ __noinline__ bool hb_decide(float xd, float yd, float zd, float xh,
+                                       float yh, float zh, float xa, float ya,
+                                       float za,
+                                       const FrameParams *__restrict__ fp,
+                                       double max_cutoff, double min_cutoff,
+                                       double angle_cutoff, int has_h,
+                                       double *d_out, double *ang_out) {
+  double v[3];
+  exact_vec<BOXKIND>(xd, yd, zd, xa, ya, za, fp, v);
+  const double d = __dsqrt_rn(__dadd_rn(
+      __dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])),
+      __dmul_rn(v[2], v[2])));
+  if (!(d <= max_cutoff)) return false;
+  if (min_cutoff >= 0.0 && !(d > min_cutoff)) return false;
+  *d_out = d;
+  *ang_out = 0.0;
+  if (!has_h) return true;
+  // calc_angles(D, H, A): rji = D - H, rjk = A - H, both minimum images
+  double rji[3], rjk[3];
+  exact_vec<BOXKIND>(xh, yh, zh, xd, yd, zd, fp, rji);
+  exact_vec<BOXKIND>(xh, yh, zh, xa, ya, za, fp, rjk);
+  const double x = __dadd_rn(
+      __dadd_rn(__dmul_rn(rji[0], rjk[0]), __dmul_rn(rji[1], rjk[1])),
+      __dmul_rn(rji[2], rjk[2]));
+  const double xp0 = __dsub_rn(__dmul_rn(rji[1], rjk[2]), __dmul_rn(rji[2], rjk[1]));
+  const double xp1 = __dadd_rn(__dmul_rn(-rji[0], rjk[2]), __dmul_rn(rji[2], rjk[0]));
+  const double xp2 = __dsub_rn(__dmul_rn(rji[0], rjk[1]), __dmul_rn(rji[1], rjk[0]));
+  const double y = __dsqrt_rn(__dadd_rn(
+      __dadd_rn(__dmul_rn(xp0, xp0), __dmul_rn(xp1, xp1)), __dmul_rn(xp2, xp2)));
+  const double ang = __dmul_rn(atan2(y, x), 57.29577951308232);  // np.rad2deg
+  *ang_out = ang;
+  return ang > angle_cutoff;
+}
+
+template <int BOXKIND, bool FILL>
+__global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
+  __shared__ __align__(16) float sx[HB_TJ], sy[HB_TJ], sz[HB_TJ];
+  __shared__ long long s_warp[8];
+  const int f = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = blockIdx.x * 256 + tid;
+  const bool valid = k < a.n_dh;
+  const FrameParams *fp = a.fparams + f;
+  const FastBox fb = load_fastbox(fp);
+  const float cut = a.header->r2_cut[1];
+  const bool slow = fp->all_slow != 0;
+  const float *gd = a.gd + (size_t)f * 3 * a.npd;
+  const float *ga = a.ga + (size_t)f * 3 * a.npa;
+  const float nan = __int_as_float(0x7fc00000);
+  // pads of the staged arrays are NaN: never a candidate
+  const float xd = valid ? gd[k] : nan, yd = valid ? gd[a.npd + k] : nan,
+              zd = valid ? gd[2 * (size_t)a.npd + k] : nan;
+  const float nxd = -xd, nyd = -yd, nzd = -zd;
+  float xh = 0.f, yh = 0.f, zh = 0.f;
+  if (a.has_h && valid) {
+    const float *gh = a.gh + (size_t)f * 3 * a.npd;
+    xh = gh[k]; yh = gh[a.npd + k]; zh = gh[2 * (size_t)a.npd + k];
+  }
+  const size_t row = (size_t)f * gridDim.x * 256 + (size_t)blockIdx.x * 256 + tid;
+  const size_t blk = (size_t)f * gridDim.x + blockIdx.x;
+
+  long long pos = 0;
+  if (FILL) {
+    // my offset = CTA offset + exclusive prefix of the row counts of the CTA
+    const uint32_t mine = a.rowcount[row];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long before = a.blocksum[blk];
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    pos = before + (long long)(incl - mine);
+    __syncthreads();
+  }
+
+  uint32_t cnt = 0;
+  auto hit = [&](int j, float xa, float ya, float za) {
+    double d, ang;
+    if (!hb_decide<BOXKIND>(xd, yd, zd, xh, yh, zh, xa, ya, za, fp, a.max_cutoff,
+                            a.min_cutoff, a.angle_cutoff, a.has_h, &d, &ang))
+      return;
+    if (FILL) {
+      const long long p = pos + cnt;
+      if (p < a.capacity) {
+        a.out_row[p] = f * a.n_dh + k;
+        a.out_acc[p] = j;
+        a.out_dist[p] = d;
+        if (a.out_angle) a.out_angle[p] = ang;
+      }
+    }
+    ++cnt;
+  };
+
+  for (int j0 = 0; j0 < a.npa; j0 += HB_TJ) {
+    const int tj = min(HB_TJ, a.npa - j0);   // multiple of 128
+    for (int t = tid; t < tj; t += 256) {
+      sx[t] = ga[j0 + t];
+      sy[t] = ga[(size_t)a.npa + j0 + t];
+      sz[t] = ga[2 * (size_t)a.npa + j0 + t];
+    }
+    __syncthreads();
+    if (!slow) {
+#pragma unroll 2
+      for (int t = 0; t < tj; t += 4) {
+        const float4 X = *reinterpret_cast<const float4 *>(sx + t);
+        const float4 Y = *reinterpret_cast<const float4 *>(sy + t);
+        const float4 Z = *reinterpret_cast<const float4 *>(sz + t);
+        const float r0 = pair_r2<BOXKIND, false>(X.x, Y.x, Z.x, nxd, nyd, nzd, fb);
+        const float r1 = pair_r2<BOXKIND, false>(X.y, Y.y, Z.y, nxd, nyd, nzd, fb);
+        const float r2 = pair_r2<BOXKIND, false>(X.z, Y.z, Z.z, nxd, nyd, nzd, fb);
+        const float r3 = pair_r2<BOXKIND, false>(X.w, Y.w, Z.w, nxd, nyd, nzd, fb);
+        if (fminf(fminf(r0, r1), fminf(r2, r3)) < cut) {
+          if (r0 < cut) hit(j0 + t, X.x, Y.x, Z.x);
+          if (r1 < cut) hit(j0 + t + 1, X.y, Y.y, Z.y);
+          if (r2 < cut) hit(j0 + t + 2, X.z, Y.z, Z.z);
+          if (r3 < cut) hit(j0 + t + 3, X.w, Y.w, Z.w);
+        }
+      }
+    } else if (valid) {
+      // frame outside the fp32 bounds (non-finite coordinates, cut-off beyond
+      // the triclinic brick, ...): every real pair takes the fp64 path
+      const int lim = min(tj, a.n_acc - j0);
+      for (int t = 0; t < lim; ++t) hit(j0 + t, sx[t], sy[t], sz[t]);
+    }
+    __syncthreads();
+  }
+
+  if (!FILL) {
+    a.rowcount[row] = cnt;
+    long long s = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_warp[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      long long tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      a.blocksum[blk] = tot;
+    }
+  }
+}
+
+// One CTA: exclusive scan of the per-CTA totals in place; grand total to
+// blocksum[n] and *total.
+__global__ __launch_bounds__(1024) void hb_scan_kernel(long long *blocksum,
+                                                       long long n,
+                                                       long long *total) {
+  __shared__ long long s_w[32];
+  __shared__ long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += 1024) {
+    const long long i = base + tid;
+    const long long v = i < n ? blocksum[i] : 0;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    long long before = s_carry;
+    for (int w = 0; w < warp; ++w) before += s_w[w];
+    if (i < n) blocksum[i] = before + incl - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = before + incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    blocksum[n] = s_carry;
+    *total = s_carry;
+  }
+}
+
+__global__ void hb_edges_kernel(double *edges, double r1) {
+  edges[0] = 0.0;
+  edges[1] = r1;
+}
+
+template <int BOXKIND>
+static int launch_hbonds(const float *xyz, int F, int natoms, const int *donors,
+                         const int *hydrogens, int n_dh, const int *acceptors,
+                         int n_acc, const float *box, double max_cutoff,
+                         double min_cutoff, double angle_cutoff,
+                         long long capacity, int *out_row, int *out_acc,
+                         double *out_dist, double *out_angle, long long *total,
+                         char *ws, const HbLayout &L, cudaStream_t st) {
+  WsHeader *header = reinterpret_cast<WsHeader *>(ws + L.header);
+  int *extents = reinterpret_cast<int *>(ws + L.extents);
+  FrameParams *fparams = reinterpret_cast<FrameParams *>(ws + L.fparams);
+  float2 *tables = reinterpret_cast<float2 *>(ws + L.tables);
+  double *edges = reinterpret_cast<double *>(ws + L.edges);
+  float *gd = reinterpret_cast<float *>(ws + L.gd);
+  float *gh = reinterpret_cast<float *>(ws + L.gh);
+  float *ga = reinterpret_cast<float *>(ws + L.ga);
+
+  init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(header, extents, F, 0);
+  hb_edges_kernel<<<1, 1, 0, st>>>(edges, max_cutoff);
+  stage_kernel<BOXKIND><<<dim3((L.npd + 255) / 256, F), 256, 0, st>>>(
+      xyz, natoms, donors, n_dh, L.npd, box, gd, extents);
+  stage_kernel<BOXKIND><<<dim3((L.npa + 255) / 256, F), 256, 0, st>>>(
+      xyz, natoms, acceptors, n_acc, L.npa, box, ga, extents);
+  if (hydrogens)
+    stage_kernel<BOXKIND><<<dim3((L.npd + 255) / 256, F), 256, 0, st>>>(
+        xyz, natoms, hydrogens, n_dh, L.npd, box, gh, extents);
+  HistParams hp;
+  hp.r0 = 0.0; hp.r1 = max_cutoff; hp.edges = edges; hp.nbins = 1;
+  // debug flag 2: bounds of the per-pair minimum image only (no shifted variant)
+  params_kernel<<<(F + 127) / 128, 128, 0, st>>>(BOXKIND, box, extents, hp, 2, F,
+                                                 fparams);
+  tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header);
+  COUNT_LAUNCH(hydrogens ? 7 : 6);
+
+  HbArgs a;
+  a.gd = gd; a.gh = gh; a.ga = ga;
+  a.npd = L.npd; a.npa = L.npa; a.n_dh = n_dh; a.n_acc = n_acc;
+  a.fparams = fparams; a.header = header;
+  a.max_cutoff = max_cutoff; a.min_cutoff = min_cutoff;
+  a.angle_cutoff = angle_cutoff;
+  a.has_h = hydrogens ? 1 : 0;
+  a.rowcount = reinterpret_cast<uint32_t *>(ws + L.rowcount);
+  a.blocksum = reinterpret_cast<long long *>(ws + L.blocksum);
+  a.capacity = capacity;
+  a.out_row = out_row; a.out_acc = out_acc;
+  a.out_dist = out_dist; a.out_angle = out_angle;
+  const dim3 grid((unsigned)L.nblk_x, (unsigned)F);
+  hb_kernel<BOXKIND, false><<<grid, 256, 0, st>>>(a);
+  hb_scan_kernel<<<1, 1024, 0, st>>>(a.blocksum, (long long)L.nblk_x * F, total);
+  hb_kernel<BOXKIND, true><<<grid, 256, 0, st>>>(a);
+  COUNT_LAUNCH(3);
+  CUDA_TRY(cudaGetLastError());
+  return RDFK_OK;
+}
+
+extern "C" size_t rdfk_hbonds_workspace_bytes(int F, int n_dh, int n_acc) {
+  if (F < 0 || n_dh < 0 || n_acc < 0) return 0;
+  return hb_layout(F, n_dh, n_acc).total;
+}
+
+extern "C" int rdfk_hbonds(const float *xyz, int F, int natoms,
+                           const int *donors, const int *hydrogens, int n_dh,
+                           const int *acceptors, int n_acc, int boxkind,
+                           const float *box, double max_cutoff,
+                           double min_cutoff, double angle_cutoff_deg,
+                           long long capacity, int *out_row, int *out_acc,
+                           double *out_dist, double *out_angle,
+                           long long *total, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+  if (F < 0 || natoms < 0 || n_dh < 0 || n_acc < 0 || capacity < 0)
+    return set_err(RDFK_EINVAL, "negative size%s%s");
+  if (!(max_cutoff > 0.0)) return set_err(RDFK_EINVAL, "need max_cutoff > 0%s%s");
+  if (boxkind < RDFK_BOX_NONE || boxkind > RDFK_BOX_TRI)
+    return set_err(RDFK_EINVAL, "bad boxkind%s%s");
+  if (!total) return set_err(RDFK_EINVAL, "null pointer argument%s%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (F == 0 || n_dh == 0 || n_acc == 0) {
+    CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(long long), st));
+    return RDFK_OK;
+  }
+  if (!xyz || !workspace || (boxkind != RDFK_BOX_NONE && !box) ||
+      (capacity > 0 && (!out_row || !out_acc || !out_dist)))
+    return set_err(RDFK_EINVAL, "null pointer argument%s%s");
+  if (F > 65535) return set_err(RDFK_EINVAL, "at most 65535 frames per call%s%s");
+  if ((long long)F * n_dh > 0x7fffffffLL)
+    return set_err(RDFK_EINVAL, "too many (frame, donor) rows in one call; "
+                                "pass fewer frames%s%s");
+  const HbLayout L = hb_layout(F, n_dh, n_acc);
+  if (workspace_bytes < L.total || ((uintptr_t)workspace & 255u))
+    return set_err(RDFK_EWORKSPACE, "workspace too small or not 256-byte "
+                                    "aligned%s%s");
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  char *ws = (char *)workspace;
+  switch (boxkind) {
+    case RDFK_BOX_NONE:
+      return launch_hbonds<RDFK_BOX_NONE>(
+          xyz, F, natoms, donors, hydrogens, n_dh, acceptors, n_acc, box,
+          max_cutoff, min_cutoff, angle_cutoff_deg, capacity, out_row, out_acc,
+          out_dist, out_angle, total, ws, L, st);
+    case RDFK_BOX_ORTHO:
+      return launch_hbonds<RDFK_BOX_ORTHO>(
+          xyz, F, natoms, donors, hydrogens, n_dh, acceptors, n_acc, box,
+          max_cutoff, min_cutoff, angle_cutoff_deg, capacity, out_row, out_acc,
+          out_dist, out_angle, total, ws, L, st);
+    default:
+      return launch_hbonds<RDFK_BOX_TRI>(
+          xyz, F, natoms, donors, hydrogens, n_dh, acceptors, n_acc, box,
+          max_cutoff, min_cutoff, angle_cutoff_deg, capacity, out_row, out_acc,
+          out_dist, out_angle, total, ws, L, st);
+  }
+}

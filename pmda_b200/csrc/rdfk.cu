@@ -2303,3 +2303,5 @@ extern "C" int rdfk_measure_fp32_peak(double *tflops_host, void *stream) {
   *tflops_host = best;
   return RDFK_OK;
 }
+
+#include "hbond.cuh"

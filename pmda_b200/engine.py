@@ -72,6 +72,8 @@ class CudaBackend(object):
     rdf_sites = staticmethod(_cabi.rdf_sites)
     contacts = staticmethod(_cabi.contacts)
     unpack_planes = staticmethod(_cabi.unpack_planes)
+    hbonds_workspace_bytes = staticmethod(_cabi.hbonds_workspace_bytes)
+    hbonds = staticmethod(_cabi.hbonds)
 
 
 _backend = CudaBackend()
@@ -989,5 +991,156 @@ def run_contacts_blocks(traj, natoms, spec, blocks, n_jobs):
         wait_end = first[b] if np.isfinite(first[b]) else time.time()
         res.append((series_np[pos:pos + n].copy(), t_io, t_c, 0.0, wait_end,
                     np.sum(t_io), np.sum(t_c)))
+        pos += n
+    return res
+
+
+# --------------------------------------------------------------------------
+# HydrogenBondAnalysis / capped_distance: ragged per-frame results
+# --------------------------------------------------------------------------
+def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
+    """All frames of one local device.  -> dict with ``rows``: list of
+    (position of the batch's first frame in the run, frames in the batch,
+    row int32, acc int32, dist float64, angle float64) host arrays."""
+    st = _state(device)
+    be = _backend
+    out = {
+        "rows": [],
+        "io": np.zeros(n_frames, dtype=np.float64),
+        "compute": np.zeros(n_frames, dtype=np.float64),
+        "first_launch": np.full(n_blocks, np.inf),
+    }
+    don, hyd, acc = spec["donors"], spec["hydrogens"], spec["acceptors"]
+    n_dh, n_acc = len(don), len(acc)
+    with st.lock:
+        cuda = st.is_cuda
+        ctx = torch.cuda.device(device) if cuda else _nullctx()
+        with ctx:
+            d_d = _to_dev_i32(don, device)
+            h_d = None if hyd is None else _to_dev_i32(hyd, device)
+            a_d = _to_dev_i32(acc, device)
+            total_d = torch.zeros(1, dtype=torch.int64, device=device)
+            pipe = _Pipeline(st, traj, natoms)
+            # keep the (frame, donor) row table of one call bounded (64 MB)
+            cap_f = max(1, (64 << 20) // max(4, 4 * n_dh))
+            pipe.batch_frames = max(1, min(pipe.batch_frames, cap_f, 65535))
+            ws = st.get_workspace(be.hbonds_workspace_bytes(
+                pipe.batch_frames, n_dh, n_acc))
+            capacity = 0
+            bufs = None
+            timers = []
+            if cuda:
+                st.compute_stream.wait_stream(torch.cuda.current_stream(device))
+            for (b, pos0, frames) in segs:
+                done = 0
+                for batch in pipe.batches(frames):
+                    B = len(batch)
+                    xyz, dims, t_io, slot = pipe.fetch(batch)
+                    kinds, box9, _ = _box_rows(dims, B)
+                    lo_f = pos0 + done
+                    out["io"][lo_f:lo_f + B] = t_io / B
+                    box_d = torch.as_tensor(box9, device=device)
+                    if cuda:
+                        st.compute_stream.wait_stream(
+                            torch.cuda.current_stream(device))
+                    out["first_launch"][b] = min(out["first_launch"][b],
+                                                 time.time())
+                    tm = _Timer(st)
+                    tm.start()
+                    stream = st.compute_stream.cuda_stream if cuda else 0
+                    sctx = torch.cuda.stream(st.compute_stream) if cuda \
+                        else _nullctx()
+                    for kind, lo, hi in _runs(kinds):
+                        want = max(4096, 2 * (hi - lo) * n_dh)
+                        while True:
+                            if capacity < want:
+                                capacity = int(want)
+                                with sctx:
+                                    bufs = (
+                                        torch.empty(capacity, dtype=torch.int32,
+                                                    device=device),
+                                        torch.empty(capacity, dtype=torch.int32,
+                                                    device=device),
+                                        torch.empty(capacity,
+                                                    dtype=torch.float64,
+                                                    device=device),
+                                        torch.empty(capacity,
+                                                    dtype=torch.float64,
+                                                    device=device))
+                            be.hbonds(xyz[lo:hi], hi - lo, natoms, d_d, h_d,
+                                      n_dh, a_d, n_acc, kind, box_d[lo:hi],
+                                      spec["max_cutoff"], spec["min_cutoff"],
+                                      spec["angle_cutoff"], capacity, bufs[0],
+                                      bufs[1], bufs[2], bufs[3], total_d, ws,
+                                      stream)
+                            with sctx:
+                                total = int(total_d.cpu()[0])   # synchronises
+                            if total <= capacity:
+                                break
+                            want = total + total // 4       # ragged: grow, redo
+                        with sctx:
+                            got = tuple(t[:total].cpu().numpy().copy()
+                                        for t in bufs)
+                        out["rows"].append((lo_f + lo, hi - lo) + got)
+                    tm.stop()
+                    pipe.mark_compute_done(slot)
+                    timers.append((tm, lo_f, B))
+                    done += B
+            for tm, lo_f, B in timers:
+                out["compute"][lo_f:lo_f + B] = tm.seconds() / B
+            if cuda:
+                st.compute_stream.synchronize()
+    return out
+
+
+def run_hbonds_blocks(traj, natoms, spec, blocks, n_jobs):
+    """Hydrogen-bond search over frame blocks.  ``spec``: ``donors`` /
+    ``hydrogens`` (paired absolute atom indices; ``hydrogens`` None = plain
+    capped_distance), ``acceptors``, ``max_cutoff``, ``min_cutoff`` (None =
+    no lower bound), ``angle_cutoff`` (degrees).  -> per-block tuples whose
+    first element is the float64 ``[n_found, 5]`` array of
+    (position of the frame in the run, D-H row k, acceptor position, distance,
+    angle), ordered by (frame, k, acceptor)."""
+    devices = _backend.devices(n_jobs)
+    n_blocks = len(blocks)
+    parts, n_frames = _shard_for_this_rank(blocks, devices)
+    n_dh = len(spec["donors"])
+
+    def fn(device, segs):
+        return _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames,
+                                spec)
+
+    outs = _run_parts(fn, devices, parts)
+    chunks = []
+    for o in outs:
+        for (pos, nf, row, acc, dist, ang) in o["rows"]:
+            tab = np.empty((len(row), 5), dtype=np.float64)
+            tab[:, 0] = pos + row // max(n_dh, 1)
+            tab[:, 1] = row % max(n_dh, 1)
+            tab[:, 2] = acc
+            tab[:, 3] = dist
+            tab[:, 4] = ang
+            chunks.append((pos, tab))
+    extra = np.stack([sum(o["io"] for o in outs),
+                      sum(o["compute"] for o in outs)])
+    if _dist_world() > 1:
+        import torch.distributed as dist
+        gathered = [None] * _dist_world()
+        dist.all_gather_object(gathered, chunks)    # ragged: one exchange
+        chunks = [c for part in gathered for c in part]
+        extra = _allreduce(torch.from_numpy(extra)).numpy()
+    chunks.sort(key=lambda c: c[0])
+    table = np.concatenate([c[1] for c in chunks]) if chunks \
+        else np.empty((0, 5), dtype=np.float64)
+    first = np.min(np.stack([o["first_launch"] for o in outs]), axis=0)
+    res, pos = [], 0
+    starts = np.searchsorted(table[:, 0], np.arange(n_frames + 1), side="left")
+    for b, blk in enumerate(blocks):
+        n = len(blk)
+        t_io = extra[0][pos:pos + n].copy()
+        t_c = extra[1][pos:pos + n].copy()
+        wait_end = first[b] if np.isfinite(first[b]) else time.time()
+        rows = table[starts[pos]:starts[pos + n]].copy()
+        res.append((rows, t_io, t_c, 0.0, wait_end, np.sum(t_io), np.sum(t_c)))
         pos += n
     return res

@@ -49,6 +49,42 @@ def water_like(n_frames, n_atoms, L, rng, sigma=0.5):
     return _clamp_ortho(pos.astype(np.float32), [L, L, L])
 
 
+def water_box(n_frames, n_mol, dimensions, rng, jitter=0.05):
+    """rigid three-site waters (O, H1, H2; O-H 0.9572 A, H-O-H 104.52 deg) at
+    random positions and orientations in the cell -> (float32 positions
+    [n_frames, 3 n_mol, 3], names).  Atom order O H H per molecule.  Molecules
+    are not wrapped as a whole: hydrogens may lie in a neighbouring image of
+    their oxygen, which is what the minimum-image angle code has to handle."""
+    from .mdamath import triclinic_vectors
+    dims = np.asarray(dimensions, dtype=np.float64)
+    m = np.asarray(triclinic_vectors(dims), dtype=np.float64)
+    frac = rng.random((n_mol, 3))
+    centre = frac @ m
+    out = np.empty((n_frames, n_mol, 3, 3), dtype=np.float64)
+    half = np.deg2rad(104.52) / 2.0
+    local = 0.9572 * np.array([[np.sin(half), np.cos(half), 0.0],
+                               [-np.sin(half), np.cos(half), 0.0]])
+    for f in range(n_frames):
+        q = rng.normal(size=(n_mol, 4))
+        q /= np.linalg.norm(q, axis=1)[:, None]
+        w, x, y, z = q.T
+        R = np.stack([
+            np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+            np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+            np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1),
+        ], 1)
+        o = centre + rng.normal(0.0, jitter * (f + 1), (n_mol, 3))
+        # wrap the oxygens into the cell through fractional coordinates
+        fo = np.mod(o @ np.linalg.inv(m), 1.0)
+        fo = np.clip(fo, 1e-5, 1.0 - 1e-5)
+        o = fo @ m
+        out[f, :, 0] = o
+        out[f, :, 1] = o + np.einsum("nij,j->ni", R, local[0])
+        out[f, :, 2] = o + np.einsum("nij,j->ni", R, local[1])
+    names = np.tile(np.array(["OW", "HW1", "HW2"]), n_mol)
+    return out.reshape(n_frames, 3 * n_mol, 3).astype(np.float32), names
+
+
 # -- the five BASELINE.json configurations ----------------------------------
 def config1(n_frames=100, n_atoms=3000, seed_extra=0):
     """InterRDF O-O, 3,000-water box, cubic L=44.78, 75 bins, range 0-15"""

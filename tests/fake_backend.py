@@ -5,7 +5,7 @@ without a GPU.  Never used by the product path."""
 import numpy as np
 import torch
 
-from oracle import c_oracle
+from oracle import c_oracle, numpy_oracle
 
 
 def _dims_from(kind, box9):
@@ -93,3 +93,35 @@ class OracleBackend(object):
                 out[f, 0] += float((1 / (1 + np.exp(beta * (d - lam * r0)))).sum())
             else:
                 out[f, :n_pairs] = torch.from_numpy(d)
+
+    @staticmethod
+    def hbonds_workspace_bytes(F, n_dh, n_acc):
+        return 256
+
+    def hbonds(self, xyz, F, natoms, donors, hydrogens, n_dh, acceptors, n_acc,
+               boxkind, box, max_cutoff, min_cutoff, angle_cutoff, capacity,
+               out_row, out_acc, out_dist, out_angle, total, workspace,
+               stream):
+        self.calls += 1
+        pos = xyz.numpy()
+        d = donors.numpy()
+        h = None if hydrogens is None else hydrogens.numpy()
+        a = acceptors.numpy()
+        n = 0
+        for f in range(F):
+            dims = None
+            if boxkind == 1:
+                dims = ("ortho", box[f].numpy()[:3].astype(np.float32))
+            elif boxkind == 2:
+                dims = ("tri_vecs",
+                        box[f].numpy().astype(np.float32).reshape(3, 3))
+            k, j, dist, ang = numpy_oracle.hbond_rows(
+                pos[f], d, h, a, dims, max_cutoff, min_cutoff, angle_cutoff)
+            for i in range(len(k)):
+                if n < capacity:
+                    out_row[n] = f * n_dh + int(k[i])
+                    out_acc[n] = int(j[i])
+                    out_dist[n] = float(dist[i])
+                    out_angle[n] = float(ang[i])
+                n += 1
+        total[0] = n

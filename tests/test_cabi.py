@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = _cabi.lib()
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.rdfk_version() == 110
+    assert lib.rdfk_version() == 120
 
 
 def test_argument_validation_needs_no_gpu():
@@ -58,6 +58,17 @@ def test_argument_validation_needs_no_gpu():
     assert rc == -1
     with pytest.raises(_cabi.RdfkError):
         _cabi.check(rc)
+    # rdfk_hbonds: cut-off, missing total, missing buffers
+    hb = lib.rdfk_hbonds
+    assert hb(None, 1, 3, None, None, 1, None, 1, 1, None, 0.0, 1.0, 150.0, 0,
+              None, None, None, None, None, None, 0, None) == -1
+    assert b"max_cutoff" in lib.rdfk_last_error()
+    assert hb(None, 1, 3, None, None, 1, None, 1, 1, None, 3.0, 1.0, 150.0, 0,
+              None, None, None, None, None, None, 0, None) == -1
+    assert hb(None, 1, 3, None, None, 1, None, 1, 7, None, 3.0, 1.0, 150.0, 0,
+              None, None, None, None, None, None, 0, None) == -1
+    assert lib.rdfk_hbonds_workspace_bytes(4, 600, 300) > 4 * 900 * 12
+    assert lib.rdfk_hbonds_workspace_bytes(-1, 1, 1) == 0
 
 
 def test_workspace_query():

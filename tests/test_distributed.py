@@ -29,6 +29,17 @@ def _make_universe():
     return Universe(pos, [L, L, L, 90, 90, 90])
 
 
+def _make_water():
+    from pmda_b200 import synthetic
+    from pmda_b200.universe import Universe
+    rng = np.random.default_rng(78)
+    dims = [15.0, 15.0, 15.0, 90, 90, 90]
+    pos, names = synthetic.water_box(5, 45, dims, rng)
+    u = Universe(pos, dims, names=names)
+    o = 3 * np.arange(45)
+    return u, np.repeat(o, 2), (o[:, None] + np.array([1, 2])).reshape(-1), o
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
@@ -53,6 +64,12 @@ def _worker(rank, world, port, out_dir):
     ags = [[u.atoms[[3]], u.atoms[10:14]], [u.atoms[[5, 6]], u.atoms[20:23]]]
     s = InterRDF_s(u, ags).run(n_blocks=2)
     res["site0"], res["site1"] = s.count[0], s.count[1]
+    from pmda_b200.hbond_analysis import HydrogenBondAnalysis
+    uw, don, hyd, acc = _make_water()
+    for nb in (1, 3):
+        hb = HydrogenBondAnalysis(uw, acceptors_sel=acc, pairs=(don, hyd))
+        hb.run(n_blocks=nb)
+        res["hbonds_nb%d" % nb] = hb.hbonds
     res["calls"] = be.calls
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **res)
     dist.barrier()
@@ -91,6 +108,16 @@ def test_two_ranks_gloo(tmp_path):
     counts, _, _ = oracle_interrdf_s(u, ags)
     assert np.array_equal(ranks[1]["site0"], counts[0])
     assert np.array_equal(ranks[1]["site1"], counts[1])
+    # ragged hydrogen-bond tables: gathered from both ranks, in frame order
+    from oracle import numpy_oracle
+    uw, don, hyd, acc = _make_water()
+    rows = np.vstack([numpy_oracle.hbonds_single_frame(
+        i, uw.trajectory[i].positions, don, hyd, acc,
+        uw.trajectory[i].dimensions) for i in range(5)])
+    assert len(rows) > 3
+    for z in ranks:
+        assert np.array_equal(z["hbonds_nb1"], rows)
+        assert np.array_equal(z["hbonds_nb3"], rows)
     # every rank did part of the work
     assert all(int(z["calls"]) > 0 for z in ranks)
 
