@@ -10,7 +10,9 @@
 //   params + tables          -> r2_cut: fp32 r2 >= r2_cut  =>  reference d > cut
 //   hb_kernel<.., false>     count the hydrogen bonds of every (frame, D-H row)
 //   hb_scan_kernel           exclusive scan of the per-CTA totals (+ grand total)
-//   hb_kernel<.., true>      same search again, rows written at their offsets
+//   hb_kernel<.., true>      rows written at their offsets: replays the screened
+//                            candidates the count pass remembered (HB_K per
+//                            row; a row with more makes its CTA scan again)
 // The result is ordered by (frame, D-H row, acceptor): the row-major order of
 // the reference's brute-force `np.where(mask)`.
 //
@@ -21,9 +23,12 @@
 // the distances are the oracle's bit for bit; angles go through CUDA's atan2
 // (<= 2 ulp from glibc's).
 
+constexpr int HB_TJ = 1024;  // acceptors staged in shared memory per round
+constexpr int HB_K = 12;     // screened candidates remembered per row
+
 struct HbLayout {
-  size_t header, extents, fparams, tables, edges, gd, gh, ga, rowcount, blocksum,
-      total;
+  size_t header, extents, fparams, tables, edges, gd, gh, ga, rowcount, ncand,
+      cand, blocksum, total;
   int npd, npa, nblk_x;
 };
 
@@ -51,6 +56,10 @@ static HbLayout hb_layout(int F, int n_dh, int n_acc) {
   off = align_up(off + sizeof(float) * 3 * (size_t)w.npa * (size_t)F, 256);
   w.rowcount = off;
   off = align_up(off + sizeof(uint32_t) * (size_t)w.nblk_x * 256 * (size_t)F, 256);
+  w.ncand = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)w.nblk_x * 256 * (size_t)F, 256);
+  w.cand = off;
+  off = align_up(off + sizeof(int) * HB_K * (size_t)w.nblk_x * 256 * (size_t)F, 256);
   w.blocksum = off;
   off = align_up(off + sizeof(long long) * ((size_t)w.nblk_x * (size_t)F + 1), 256);
   w.total = off;
@@ -111,14 +120,14 @@ struct HbArgs {
   const WsHeader *header;
   double max_cutoff, min_cutoff, angle_cutoff;  // min_cutoff < 0: none
   int has_h;
-  uint32_t *rowcount;     // [F][nblk_x * 256]
+  uint32_t *rowcount;     // [F][nblk_x * 256] hydrogen bonds of the row
+  uint32_t *ncand;        // [F][nblk_x * 256] pairs that passed the fp32 screen
+  int *cand;              // [F][nblk_x * 256][HB_K] the first HB_K of them
   long long *blocksum;    // [F * nblk_x + 1]: totals, then exclusive offsets
   long long capacity;
   int *out_row, *out_acc;
   double *out_dist, *out_angle;
 };
-
-constexpr int HB_TJ = 1024;  // acceptors staged in shared memory per round
 
 // One candidate of the fp32 screen, decided with the reference arithmetic.
 // Returns true for a hydrogen bond (or a capped pair when there is no
@@ -203,8 +212,12 @@ __global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
     __syncthreads();
   }
 
-  uint32_t cnt = 0;
+  uint32_t cnt = 0, nc = 0;
   auto hit = [&](int j, float xa, float ya, float za) {
+    if (!FILL) {
+      if (nc < (uint32_t)HB_K) a.cand[row * HB_K + nc] = j;
+      ++nc;
+    }
     double d, ang;
     if (!hb_decide<BOXKIND>(xd, yd, zd, xh, yh, zh, xa, ya, za, fp, a.max_cutoff,
                             a.min_cutoff, a.angle_cutoff, a.has_h, &d, &ang))
@@ -221,6 +234,24 @@ __global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
     ++cnt;
   };
 
+  // Fill pass: rows without a hydrogen bond have nothing to write; the others
+  // replay the candidates the count pass remembered.  Only a row with more
+  // than HB_K candidates (or an fp64-only frame) makes its CTA scan again.
+  bool rescan = true;
+  if (FILL) {
+    const uint32_t want = a.rowcount[row];
+    const uint32_t have = a.ncand[row];
+    const bool over = want > 0 && have > (uint32_t)HB_K;
+    if (want > 0 && !over) {
+      for (uint32_t c = 0; c < have; ++c) {
+        const int j = a.cand[row * HB_K + c];
+        hit(j, ga[j], ga[(size_t)a.npa + j], ga[2 * (size_t)a.npa + j]);
+      }
+    }
+    rescan = over;
+    if (!__syncthreads_or(over ? 1 : 0)) return;
+  }
+
   for (int j0 = 0; j0 < a.npa; j0 += HB_TJ) {
     const int tj = min(HB_TJ, a.npa - j0);   // multiple of 128
     for (int t = tid; t < tj; t += 256) {
@@ -229,7 +260,9 @@ __global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
       sz[t] = ga[2 * (size_t)a.npa + j0 + t];
     }
     __syncthreads();
-    if (!slow) {
+    if (!rescan) {
+      // (fill pass) another row of this CTA needs the scan, mine does not
+    } else if (!slow) {
 #pragma unroll 2
       for (int t = 0; t < tj; t += 4) {
         const float4 X = *reinterpret_cast<const float4 *>(sx + t);
@@ -257,6 +290,7 @@ __global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
 
   if (!FILL) {
     a.rowcount[row] = cnt;
+    a.ncand[row] = nc;
     long long s = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -351,6 +385,8 @@ static int launch_hbonds(const float *xyz, int F, int natoms, const int *donors,
   a.angle_cutoff = angle_cutoff;
   a.has_h = hydrogens ? 1 : 0;
   a.rowcount = reinterpret_cast<uint32_t *>(ws + L.rowcount);
+  a.ncand = reinterpret_cast<uint32_t *>(ws + L.ncand);
+  a.cand = reinterpret_cast<int *>(ws + L.cand);
   a.blocksum = reinterpret_cast<long long *>(ws + L.blocksum);
   a.capacity = capacity;
   a.out_row = out_row; a.out_acc = out_acc;

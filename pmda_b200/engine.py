@@ -1021,8 +1021,8 @@ def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
             a_d = _to_dev_i32(acc, device)
             total_d = torch.zeros(1, dtype=torch.int64, device=device)
             pipe = _Pipeline(st, traj, natoms)
-            # keep the (frame, donor) row table of one call bounded (64 MB)
-            cap_f = max(1, (64 << 20) // max(4, 4 * n_dh))
+            # keep the (frame, donor) row tables of one call bounded (256 MB)
+            cap_f = max(1, (256 << 20) // max(56, 56 * n_dh))
             pipe.batch_frames = max(1, min(pipe.batch_frames, cap_f, 65535))
             ws = st.get_workspace(be.hbonds_workspace_bytes(
                 pipe.batch_frames, n_dh, n_acc))
