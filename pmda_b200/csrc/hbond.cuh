@@ -8,7 +8,9 @@
 // Per call (F frames):
 //   stage donors, hydrogens, acceptors (gather, AoS -> SoA, triclinic wrap)
 //   params + tables          -> r2_cut: fp32 r2 >= r2_cut  =>  reference d > cut
-//   hb_kernel<.., false>     count the hydrogen bonds of every (frame, D-H row)
+//   hb_kernel<.., false>     fp32 screen of every (frame, D-H row) against all
+//                            acceptors; the few survivors are remembered
+//                            (HB_K per row), then decided in fp64 -> row counts
 //   hb_scan_kernel           exclusive scan of the per-CTA totals (+ grand total)
 //   hb_kernel<.., true>      rows written at their offsets: replays the screened
 //                            candidates the count pass remembered (HB_K per
@@ -213,11 +215,9 @@ __global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
   }
 
   uint32_t cnt = 0, nc = 0;
-  auto hit = [&](int j, float xa, float ya, float za) {
-    if (!FILL) {
-      if (nc < (uint32_t)HB_K) a.cand[row * HB_K + nc] = j;
-      ++nc;
-    }
+  // a pair that passed the fp32 screen (or any pair of an fp64-only frame):
+  // the reference decision, and in the fill pass the output row
+  auto decide = [&](int j, float xa, float ya, float za) {
     double d, ang;
     if (!hb_decide<BOXKIND>(xd, yd, zd, xh, yh, zh, xa, ya, za, fp, a.max_cutoff,
                             a.min_cutoff, a.angle_cutoff, a.has_h, &d, &ang))
@@ -233,59 +233,82 @@ __global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
     }
     ++cnt;
   };
+  int *my_cand = a.cand + row * HB_K;
 
-  // Fill pass: rows without a hydrogen bond have nothing to write; the others
-  // replay the candidates the count pass remembered.  Only a row with more
-  // than HB_K candidates (or an fp64-only frame) makes its CTA scan again.
-  bool rescan = true;
-  if (FILL) {
-    const uint32_t want = a.rowcount[row];
-    const uint32_t have = a.ncand[row];
-    const bool over = want > 0 && have > (uint32_t)HB_K;
-    if (want > 0 && !over) {
-      for (uint32_t c = 0; c < have; ++c) {
-        const int j = a.cand[row * HB_K + c];
-        hit(j, ga[j], ga[(size_t)a.npa + j], ga[2 * (size_t)a.npa + j]);
+  // Phase A (count pass): the fp32 screen.  Candidates are only remembered
+  // here -- deciding them inside the loop would run the fp64 code with one
+  // active lane per warp.
+  if (!FILL) {
+    if (slow) {
+      nc = valid ? HB_K + 1 : 0;      // no screen: straight to phase C
+    } else {
+      auto push = [&](int j) {
+        if (nc < (uint32_t)HB_K) my_cand[nc] = j;
+        ++nc;
+      };
+      for (int j0 = 0; j0 < a.npa; j0 += HB_TJ) {
+        const int tj = min(HB_TJ, a.npa - j0);   // multiple of 128
+        for (int t = tid; t < tj; t += 256) {
+          sx[t] = ga[j0 + t];
+          sy[t] = ga[(size_t)a.npa + j0 + t];
+          sz[t] = ga[2 * (size_t)a.npa + j0 + t];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int t = 0; t < tj; t += 4) {
+          const float4 X = *reinterpret_cast<const float4 *>(sx + t);
+          const float4 Y = *reinterpret_cast<const float4 *>(sy + t);
+          const float4 Z = *reinterpret_cast<const float4 *>(sz + t);
+          const float r0 = pair_r2<BOXKIND, false>(X.x, Y.x, Z.x, nxd, nyd, nzd, fb);
+          const float r1 = pair_r2<BOXKIND, false>(X.y, Y.y, Z.y, nxd, nyd, nzd, fb);
+          const float r2 = pair_r2<BOXKIND, false>(X.z, Y.z, Z.z, nxd, nyd, nzd, fb);
+          const float r3 = pair_r2<BOXKIND, false>(X.w, Y.w, Z.w, nxd, nyd, nzd, fb);
+          if (fminf(fminf(r0, r1), fminf(r2, r3)) < cut) {
+            if (r0 < cut) push(j0 + t);
+            if (r1 < cut) push(j0 + t + 1);
+            if (r2 < cut) push(j0 + t + 2);
+            if (r3 < cut) push(j0 + t + 3);
+          }
+        }
+        __syncthreads();
       }
     }
-    rescan = over;
-    if (!__syncthreads_or(over ? 1 : 0)) return;
+  } else {
+    // fill pass: rows without a hydrogen bond have nothing to write
+    nc = a.rowcount[row] > 0 ? a.ncand[row] : 0;
   }
 
-  for (int j0 = 0; j0 < a.npa; j0 += HB_TJ) {
-    const int tj = min(HB_TJ, a.npa - j0);   // multiple of 128
-    for (int t = tid; t < tj; t += 256) {
-      sx[t] = ga[j0 + t];
-      sy[t] = ga[(size_t)a.npa + j0 + t];
-      sz[t] = ga[2 * (size_t)a.npa + j0 + t];
+  // Phase B: decide the remembered candidates, lanes side by side.
+  const bool over = nc > (uint32_t)HB_K;
+  if (!over) {
+    for (uint32_t c = 0; c < nc; ++c) {
+      const int j = my_cand[c];
+      decide(j, ga[j], ga[(size_t)a.npa + j], ga[2 * (size_t)a.npa + j]);
     }
-    __syncthreads();
-    if (!rescan) {
-      // (fill pass) another row of this CTA needs the scan, mine does not
-    } else if (!slow) {
-#pragma unroll 2
-      for (int t = 0; t < tj; t += 4) {
-        const float4 X = *reinterpret_cast<const float4 *>(sx + t);
-        const float4 Y = *reinterpret_cast<const float4 *>(sy + t);
-        const float4 Z = *reinterpret_cast<const float4 *>(sz + t);
-        const float r0 = pair_r2<BOXKIND, false>(X.x, Y.x, Z.x, nxd, nyd, nzd, fb);
-        const float r1 = pair_r2<BOXKIND, false>(X.y, Y.y, Z.y, nxd, nyd, nzd, fb);
-        const float r2 = pair_r2<BOXKIND, false>(X.z, Y.z, Z.z, nxd, nyd, nzd, fb);
-        const float r3 = pair_r2<BOXKIND, false>(X.w, Y.w, Z.w, nxd, nyd, nzd, fb);
-        if (fminf(fminf(r0, r1), fminf(r2, r3)) < cut) {
-          if (r0 < cut) hit(j0 + t, X.x, Y.x, Z.x);
-          if (r1 < cut) hit(j0 + t + 1, X.y, Y.y, Z.y);
-          if (r2 < cut) hit(j0 + t + 2, X.z, Y.z, Z.z);
-          if (r3 < cut) hit(j0 + t + 3, X.w, Y.w, Z.w);
+  }
+
+  // Phase C: a row with more than HB_K candidates (or an fp64-only frame)
+  // makes its CTA walk the acceptors again, deciding in place.
+  if (__syncthreads_or(over ? 1 : 0)) {
+    for (int j0 = 0; j0 < a.npa; j0 += HB_TJ) {
+      const int tj = min(HB_TJ, a.npa - j0);
+      for (int t = tid; t < tj; t += 256) {
+        sx[t] = ga[j0 + t];
+        sy[t] = ga[(size_t)a.npa + j0 + t];
+        sz[t] = ga[2 * (size_t)a.npa + j0 + t];
+      }
+      __syncthreads();
+      if (over) {
+        const int lim = min(tj, a.n_acc - j0);
+        for (int t = 0; t < lim; ++t) {
+          if (!slow &&
+              !(pair_r2<BOXKIND, false>(sx[t], sy[t], sz[t], nxd, nyd, nzd, fb) < cut))
+            continue;
+          decide(j0 + t, sx[t], sy[t], sz[t]);
         }
       }
-    } else if (valid) {
-      // frame outside the fp32 bounds (non-finite coordinates, cut-off beyond
-      // the triclinic brick, ...): every real pair takes the fp64 path
-      const int lim = min(tj, a.n_acc - j0);
-      for (int t = 0; t < lim; ++t) hit(j0 + t, sx[t], sy[t], sz[t]);
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   if (!FILL) {
