@@ -1140,7 +1140,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   static_assert(RI == 4 && GJ == 8 && GPC == 16, "written for 4 x 8, 16 groups");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ HistParams s_hp;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so
+  // branches on per-warp shared-memory words need no convergence barriers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   unsigned char *wbase = smem_raw + (size_t)warp * SM_WARP;
   float *q = reinterpret_cast<float *>(wbase);
   float *jst = reinterpret_cast<float *>(wbase + SM_Q);
@@ -1197,8 +1200,9 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     ++n_items;
     const int f = item / a.ncl_i, ic = item - f * a.ncl_i;
     const FrameParams *fp = a.fparams + f;
-    const int all_slow = fp->all_slow;
-    const int shift_ok = fp->shift_ok;
+    // (or-reductions of identical values: provably warp-uniform flags)
+    const int all_slow = __reduce_or_sync(0xffffffffu, fp->all_slow);
+    const int shift_ok = __reduce_or_sync(0xffffffffu, fp->shift_ok);
     const size_t np_i = (size_t)a.np_i, np_j = (size_t)a.np_j;
     const float *gi_cl = a.gi + (size_t)f * 3 * np_i + (size_t)ic * CI;
     const float *gj_f = a.gj + (size_t)f * 3 * np_j;
@@ -1457,7 +1461,9 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
 
     // evaluate staged j-group `slot` against my RI i-atoms
     auto evaluate = [&](int slot) {
-      const int packed = jcode[slot];
+      // or-reduction of 32 identical words: a no-op that proves to the compiler
+      // that the word (and every branch on it) is warp-uniform
+      const int packed = __reduce_or_sync(0xffffffffu, jcode[slot]);
       const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
                 code = (packed >> 24) & 0x7f;
       const float *js = jst + slot * 3 * GJ;
