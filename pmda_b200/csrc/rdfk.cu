@@ -1494,14 +1494,16 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       }
       // room for this group (8 pairs per active quarter) in every lane's
       // queue, and for one more entry in the log?
-      if (nlog == LOGMAX ||
-          __any_sync(0xffffffffu,
-                     qaddr > qbase + (QS - GJ * __popc(qmask)) * 128))
+      // (one vote for both conditions: its result is uniform for the compiler,
+      // so the branch around the drain needs no convergence barrier)
+      if (__any_sync(0xffffffffu,
+                     (nlog == LOGMAX) |
+                         (qaddr > qbase + (QS - GJ * __popc(qmask)) * 128)))
         drain();
       if (lane == 0) glog[nlog] = packed;
       mark[nlog * 32 + lane] = (unsigned char)((qaddr - qbase) >> 7);
       ++nlog;
-      if (code != cur_code) {
+      if (__any_sync(0xffffffffu, code != cur_code)) {
         float sx = 0.f, sy = 0.f, sz = 0.f;
         if (BOXKIND != RDFK_BOX_NONE && (code & CODE_PLAIN)) {
           const FastBox fbs = load_fastbox(fp);
