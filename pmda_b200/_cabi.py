@@ -8,7 +8,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librdfk.so")
+#: RDFK_LIB selects another build of the same sources (kernel experiments)
+LIB_PATH = os.environ.get("RDFK_LIB") or os.path.join(_HERE, "csrc",
+                                                      "librdfk.so")
 
 BOX_NONE, BOX_ORTHO, BOX_TRI = 0, 1, 2
 

@@ -40,14 +40,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """`out` / `defines`: experimental variants next to the default library
+    (selected at run time with RDFK_LIB)"""
+    if out is None and not force and not needs_build():
         return OUT
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) \
-        + SOURCES + ["-o", OUT]
+        + ["-D" + d for d in defines] + SOURCES + ["-o", out or OUT]
     subprocess.check_call(cmd)
-    return OUT
+    return out or OUT
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _out = [a[6:] for a in sys.argv if a.startswith("--out=")]
+    _def = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
+                out=_out[0] if _out else None, defines=_def))

@@ -1178,6 +1178,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   const uint32_t wh_s = GLOBAL_HIST ? 0u : smem_u32(wh);
   const unsigned int sharers = GLOBAL_HIST ? 1 : (NWARP + copies - 1) / copies;
   const unsigned int flush_limit = (1u << 30) / sharers;
+  const uint32_t glog_s = smem_u32(glog), mark_s = smem_u32(mark) + lane;
   const uint32_t qbase = smem_u32(q + lane);
   uint32_t qaddr = qbase;
   const unsigned int lt_mask = (1u << lane) - 1u;
@@ -1460,10 +1461,13 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     auto drain_small = [&]() { drain_w(std::integral_constant<int, 2>()); };
 
     // evaluate staged j-group `slot` against my RI i-atoms
-    auto evaluate = [&](int slot) {
+    // `packed` = group_word(slot): fetched one group ahead by the caller
+    auto group_word = [&](int slot) -> int {
       // or-reduction of 32 identical words: a no-op that proves to the compiler
       // that the word (and every branch on it) is warp-uniform
-      const int packed = __reduce_or_sync(0xffffffffu, jcode[slot]);
+      return __reduce_or_sync(0xffffffffu, jcode[slot]);
+    };
+    auto evaluate = [&](int slot, const int packed) {
       const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
                 code = (packed >> 24) & 0x7f;
       const float *js = jst + slot * 3 * GJ;
@@ -1500,8 +1504,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                      (nlog == LOGMAX) |
                          (qaddr > qbase + (QS - GJ * __popc(qmask)) * 128)))
         drain();
-      if (lane == 0) glog[nlog] = packed;
-      mark[nlog * 32 + lane] = (unsigned char)((qaddr - qbase) >> 7);
+      // (shared-window addresses: a generic store recomputes the window base)
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(glog_s + 4u * nlog), "r"(packed));
+      asm volatile("st.shared.u8 [%0], %1;" ::"r"(mark_s + 32u * nlog),
+                   "r"((qaddr - qbase) >> 7));
       ++nlog;
       if (__any_sync(0xffffffffu, code != cur_code)) {
         float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -1661,7 +1667,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
           cp_async_commit_wait_all();
           __syncwarp();
 #pragma unroll 1
-          for (int h = 0; h < nh; ++h) evaluate(h);
+          for (int h = 0; h < nh; ++h) evaluate(h, group_word(h));
         }
       }
       if (!all_slow) drain_small();
