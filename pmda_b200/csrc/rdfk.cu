@@ -1098,14 +1098,17 @@ __device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float nxi
 // eight j-atoms in order.
 template <int BOXKIND>
 __device__ __noinline__ int resolve_entry(
-    int s, int lane, const unsigned char *mark, const int *glog, int nlog,
+    int s, int col, const unsigned char *mark, const int *glog, int nlog,
     const float *gi_cl, size_t np_i, const float *gj_f, size_t np_j,
     int swapped, float cut, const FrameParams *__restrict__ fp,
     const HistParams *__restrict__ hp) {
+  // `col`: the queue column the entry sits in.  Columns rotate one lane per
+  // logged group, so the lane that pushed into it at log entry e was col + e.
   int e = 0;
   for (int t = 1; t < nlog; ++t)
-    if ((int)mark[t * 32 + lane] <= s) e = t;
-  int rank = s - (int)mark[e * 32 + lane];
+    if ((int)mark[t * 32 + col] <= s) e = t;
+  int rank = s - (int)mark[e * 32 + col];
+  const int lane = (col + e) & 31;
   const int packed = glog[e];
   const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
             code = (packed >> 24) & 0x7f;
@@ -1178,7 +1181,8 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   const uint32_t wh_s = GLOBAL_HIST ? 0u : smem_u32(wh);
   const unsigned int sharers = GLOBAL_HIST ? 1 : (NWARP + copies - 1) / copies;
   const unsigned int flush_limit = (1u << 30) / sharers;
-  const uint32_t glog_s = smem_u32(glog), mark_s = smem_u32(mark) + lane;
+  const uint32_t glog_s = smem_u32(glog), mark_s = smem_u32(mark);
+  const uint32_t qw_s = smem_u32(q);   // row r, column c: qw_s + 128 r + 4 c
   const uint32_t qbase = smem_u32(q + lane);
   uint32_t qaddr = qbase;
   const unsigned int lt_mask = (1u << lane) - 1u;
@@ -1380,7 +1384,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     auto drain_w = [&](auto width_tag) {
       constexpr int DWL = decltype(width_tag)::value;
       __syncwarp();   // the group log was written by lane 0
-      const int n = (int)((qaddr - qbase) >> 7);
+      // my current column (the pointers rotate one lane per logged group)
+      const int col = (lane - nlog) & 31;
+      const int n = (int)((qaddr - qw_s) >> 7);
+      const float *qcol = q + col;
       const int nmax = __reduce_max_sync(0xffffffffu, n);
       const float inv_dr = fp->inv_dr, koffm = fp->koffm;
       const unsigned int toff = cls ? (unsigned int)nb1 + 1u : 1u;
@@ -1388,7 +1395,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       for (int s = 0; s < nmax; s += DWL) {
         float v[DWL];
 #pragma unroll
-        for (int u = 0; u < DWL; ++u) v[u] = q[(s + u) * 32 + lane];
+        for (int u = 0; u < DWL; ++u) v[u] = qcol[(s + u) * 32];
         unsigned int okmask = 0u;
         const int rem = n - s;   // entries s .. s + rem - 1 are live
 #pragma unroll
@@ -1436,7 +1443,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         while (failmask) {
           const int se = __ffsll((long long)failmask) - 1;
           failmask &= failmask - 1;
-          const int kk = resolve_entry<BOXKIND>(se, lane, mark, glog, nlog, gi_cl,
+          const int kk = resolve_entry<BOXKIND>(se, col, mark, glog, nlog, gi_cl,
                                                 np_i, gj_f, np_j, a.swapped, cut,
                                                 fp, &s_hp);
           ++n_slow;
@@ -1502,12 +1509,13 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       // so the branch around the drain needs no convergence barrier)
       if (__any_sync(0xffffffffu,
                      (nlog == LOGMAX) |
-                         (qaddr > qbase + (QS - GJ * __popc(qmask)) * 128)))
+                         (qaddr > qw_s + (QS - GJ * __popc(qmask)) * 128 + 127)))
         drain();
       // (shared-window addresses: a generic store recomputes the window base)
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(glog_s + 4u * nlog), "r"(packed));
-      asm volatile("st.shared.u8 [%0], %1;" ::"r"(mark_s + 32u * nlog),
-                   "r"((qaddr - qbase) >> 7));
+      asm volatile("st.shared.u8 [%0], %1;" ::"r"(mark_s + 32u * nlog +
+                                                   ((lane - nlog) & 31)),
+                   "r"((qaddr - qw_s) >> 7));
       ++nlog;
       if (__any_sync(0xffffffffu, code != cur_code)) {
         float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -1579,6 +1587,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                    cut);
         }
       }
+      // hand my queue column to the next lane: every column collects the hits
+      // of many different i-atoms, so the columns fill evenly and the rows the
+      // drain walks are denser
+      qaddr = __shfl_sync(0xffffffffu, qaddr, (lane + 31) & 31);
     };
 
     // Level 1: 32 j-clusters per round against my cluster box.  Level 2: the
