@@ -356,7 +356,7 @@ def run_b200(args):
     # is not the one the capture was taken on
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r1h_traffic.json")) as fh:
             tr = json.load(fh)
         if args.n_atoms == N_ATOMS:
             traffic = tr["dram_bytes_per_frame"] * frames_per_launch
@@ -369,7 +369,7 @@ def run_b200(args):
         "bound": "fp32", "kernel": "pair_prune_kernel<ORTHO>",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": traffic,
-        "traffic_source": "profiles/r1c_traffic.json: dram__bytes_read+write of "
+        "traffic_source": "profiles/r1h_traffic.json: dram__bytes_read+write of "
                           "one ncu --set full capture, per frame x frames per "
                           "launch",
         "peak_source": "FFMA loop measured live (rdfk_measure_fp32_peak); "
