@@ -8,13 +8,17 @@
 // Per call (F frames):
 //   stage donors, hydrogens, acceptors (gather, AoS -> SoA, triclinic wrap)
 //   params + tables          -> r2_cut: fp32 r2 >= r2_cut  =>  reference d > cut
-//   hb_kernel<.., false>     fp32 screen of every (frame, D-H row) against all
-//                            acceptors; the few survivors are remembered
+//   hb_cell_count / scan / hb_cell_scatter
+//                            acceptors counting-sorted into a cell grid whose
+//                            cells are at least the cut-off wide
+//   hb_cells_kernel<false>   every (frame, D-H row) walks the 27 cells around
+//                            its donor: fp32 screen, survivors remembered
 //                            (HB_K per row), then decided in fp64 -> row counts
 //   hb_scan_kernel           exclusive scan of the per-CTA totals (+ grand total)
-//   hb_kernel<.., true>      rows written at their offsets: replays the screened
-//                            candidates the count pass remembered (HB_K per
-//                            row; a row with more makes its CTA scan again)
+//   hb_cells_kernel<true>    rows written at their offsets: replays the
+//                            remembered candidates (a row with more walks again)
+//   (RDFK_DEBUG bit 0: hb_kernel instead -- no grid, every acceptor, tiled
+//   through shared memory; same results)
 // The result is ordered by (frame, D-H row, acceptor): the row-major order of
 // the reference's brute-force `np.where(mask)`.
 //
@@ -27,10 +31,12 @@
 
 constexpr int HB_TJ = 1024;  // acceptors staged in shared memory per round
 constexpr int HB_K = 12;     // screened candidates remembered per row
+constexpr int HB_NKMAX = 32;                                   // cells per axis
+constexpr int HB_NCS = HB_NKMAX * HB_NKMAX * HB_NKMAX + 1;     // + end marker
 
 struct HbLayout {
   size_t header, extents, fparams, tables, edges, gd, gh, ga, rowcount, ncand,
-      cand, blocksum, total;
+      cand, blocksum, cells, cid, crank, sorted, total;
   int npd, npa, nblk_x;
 };
 
@@ -64,6 +70,16 @@ static HbLayout hb_layout(int F, int n_dh, int n_acc) {
   off = align_up(off + sizeof(int) * HB_K * (size_t)w.nblk_x * 256 * (size_t)F, 256);
   w.blocksum = off;
   off = align_up(off + sizeof(long long) * ((size_t)w.nblk_x * (size_t)F + 1), 256);
+  // acceptor cell grid: per-frame cell starts, per-atom cell and arrival rank,
+  // acceptors in cell order as (x, y, z, index)
+  w.cells = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)HB_NCS * (size_t)F, 256);
+  w.cid = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)w.npa * (size_t)F, 256);
+  w.crank = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)w.npa * (size_t)F, 256);
+  w.sorted = off;
+  off = align_up(off + sizeof(float4) * (size_t)w.npa * (size_t)F, 256);
   w.total = off;
   return w;
 }
@@ -126,6 +142,8 @@ struct HbArgs {
   uint32_t *ncand;        // [F][nblk_x * 256] pairs that passed the fp32 screen
   int *cand;              // [F][nblk_x * 256][HB_K] the first HB_K of them
   long long *blocksum;    // [F * nblk_x + 1]: totals, then exclusive offsets
+  const uint32_t *cells;  // [F][HB_NCS] cell starts (exclusive scan of counts)
+  const float4 *sorted;   // [F][npa] acceptors in cell order: x, y, z, index
   long long capacity;
   int *out_row, *out_acc;
   double *out_dist, *out_angle;
@@ -361,6 +379,237 @@ __global__ __launch_bounds__(1024) void hb_scan_kernel(long long *blocksum,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Cell grid over the acceptors.  Cells live in the RDF path's "prune space"
+// (FrameParams: Cartesian offset wrapped into the box, or triclinic fractional
+// coordinates), at least `rprune` (cut-off + fp32 slack) wide in every
+// direction, so every acceptor within the cut-off of a donor sits in one of the
+// 27 cells around the donor's.  A periodic axis with fewer than 3 cells, and
+// every axis of a frame without usable bounds, gets a single cell.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void hb_grid(const FrameParams &p, int nk[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int n = 1;
+    if (p.prune_ok && !p.all_slow && p.gscale[k] > 0.f) {
+      const float cells = __fdiv_rd(p.wk[k], __fmul_ru(p.gscale[k], p.rprune));
+      n = cells >= (float)HB_NKMAX ? HB_NKMAX : (cells >= 1.f ? (int)cells : 1);
+      if (p.per[k] < INFINITY && n < 3) n = 1;
+    }
+    nk[k] = n;
+  }
+}
+
+template <int BOXKIND>
+__device__ __forceinline__ void hb_cell_of(float x, float y, float z,
+                                           const FrameParams &p, const int nk[3],
+                                           int c[3]) {
+  float u[3];
+  prune_coords<BOXKIND>(x, y, z, p, u[0], u[1], u[2]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    // NaN -> 0; a coordinate that rounds just outside the grid is clamped into
+    // the edge cell, a neighbour of the cell it belongs to
+    const int v = __float2int_rd(__fmul_rn(__fmul_rn(u[k], p.gscale[k]), (float)nk[k]));
+    c[k] = max(0, min(nk[k] - 1, v));
+  }
+}
+
+template <int BOXKIND>
+__global__ __launch_bounds__(256) void hb_cell_count_kernel(
+    const float *__restrict__ ga, int n, int np,
+    const FrameParams *__restrict__ fparams, uint32_t *__restrict__ cells,
+    uint32_t *__restrict__ cid, uint32_t *__restrict__ crank) {
+  const int f = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const FrameParams &p = fparams[f];
+  const float *g = ga + (size_t)f * 3 * np;
+  int nk[3], c[3];
+  hb_grid(p, nk);
+  hb_cell_of<BOXKIND>(g[a], g[(size_t)np + a], g[2 * (size_t)np + a], p, nk, c);
+  const uint32_t id = (uint32_t)((c[2] * nk[1] + c[1]) * nk[0] + c[0]);
+  cid[(size_t)f * np + a] = id;
+  crank[(size_t)f * np + a] = atomicAdd(cells + (size_t)f * HB_NCS + id, 1u);
+}
+
+__global__ __launch_bounds__(256) void hb_cell_scatter_kernel(
+    const float *__restrict__ ga, int n, int np,
+    const uint32_t *__restrict__ cells, const uint32_t *__restrict__ cid,
+    const uint32_t *__restrict__ crank, float4 *__restrict__ sorted) {
+  const int f = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const float *g = ga + (size_t)f * 3 * np;
+  const uint32_t pos = cells[(size_t)f * HB_NCS + cid[(size_t)f * np + a]] +
+                       crank[(size_t)f * np + a];
+  sorted[(size_t)f * np + pos] =
+      make_float4(g[a], g[(size_t)np + a], g[2 * (size_t)np + a], __int_as_float(a));
+}
+
+// One thread per (frame, D-H row): walk the 27 cells around the donor.  Same
+// two passes and the same candidate replay as hb_kernel; a row's bonds come
+// out in cell order and are sorted by acceptor index at the end of the fill.
+template <int BOXKIND, bool FILL>
+__global__ __launch_bounds__(256) void hb_cells_kernel(const HbArgs a) {
+  __shared__ long long s_warp[8];
+  const int f = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = blockIdx.x * 256 + tid;
+  const bool valid = k < a.n_dh;
+  const FrameParams *fp = a.fparams + f;
+  const FastBox fb = load_fastbox(fp);
+  const float cut = a.header->r2_cut[1];
+  const bool slow = fp->all_slow != 0;
+  const float *gd = a.gd + (size_t)f * 3 * a.npd;
+  const float4 *sa = a.sorted + (size_t)f * a.npa;
+  const uint32_t *cs = a.cells + (size_t)f * HB_NCS;
+  const float nan = __int_as_float(0x7fc00000);
+  const float xd = valid ? gd[k] : nan, yd = valid ? gd[a.npd + k] : nan,
+              zd = valid ? gd[2 * (size_t)a.npd + k] : nan;
+  const float nxd = -xd, nyd = -yd, nzd = -zd;
+  float xh = 0.f, yh = 0.f, zh = 0.f;
+  if (a.has_h && valid) {
+    const float *gh = a.gh + (size_t)f * 3 * a.npd;
+    xh = gh[k]; yh = gh[a.npd + k]; zh = gh[2 * (size_t)a.npd + k];
+  }
+  const size_t row = (size_t)f * gridDim.x * 256 + (size_t)blockIdx.x * 256 + tid;
+  const size_t blk = (size_t)f * gridDim.x + blockIdx.x;
+
+  long long pos = 0;
+  if (FILL) {
+    const uint32_t mine = a.rowcount[row];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long before = a.blocksum[blk];
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    pos = before + (long long)(incl - mine);
+  }
+
+  uint32_t cnt = 0, nc = 0;
+  auto decide = [&](const float4 A) {
+    double d, ang;
+    if (!hb_decide<BOXKIND>(xd, yd, zd, xh, yh, zh, A.x, A.y, A.z, fp, a.max_cutoff,
+                            a.min_cutoff, a.angle_cutoff, a.has_h, &d, &ang))
+      return;
+    if (FILL) {
+      const long long p = pos + cnt;
+      if (p < a.capacity) {
+        a.out_row[p] = f * a.n_dh + k;
+        a.out_acc[p] = __float_as_int(A.w);
+        a.out_dist[p] = d;
+        if (a.out_angle) a.out_angle[p] = ang;
+      }
+    }
+    ++cnt;
+  };
+  int *my_cand = a.cand + row * HB_K;
+
+  // the cells around mine; `each(lo, hi)` gets their ranges of `sorted`
+  int nk[3], c[3];
+  hb_grid(*fp, nk);
+  hb_cell_of<BOXKIND>(xd, yd, zd, *fp, nk, c);
+  auto walk = [&](auto &&each) {
+    for (int dz = -1; dz <= 1; ++dz) {
+      int z = c[2] + dz;
+      if (nk[2] == 1 ? dz != 0 : false) continue;
+      if (z < 0 || z >= nk[2]) {
+        if (!(fp->per[2] < INFINITY)) continue;
+        z += z < 0 ? nk[2] : -nk[2];
+      }
+      for (int dy = -1; dy <= 1; ++dy) {
+        int y = c[1] + dy;
+        if (nk[1] == 1 ? dy != 0 : false) continue;
+        if (y < 0 || y >= nk[1]) {
+          if (!(fp->per[1] < INFINITY)) continue;
+          y += y < 0 ? nk[1] : -nk[1];
+        }
+        // the (up to) three x cells are contiguous unless they wrap
+        for (int dx = -1; dx <= 1; ++dx) {
+          int x = c[0] + dx;
+          if (nk[0] == 1 ? dx != 0 : false) continue;
+          if (x < 0 || x >= nk[0]) {
+            if (!(fp->per[0] < INFINITY)) continue;
+            x += x < 0 ? nk[0] : -nk[0];
+          }
+          const int id = (z * nk[1] + y) * nk[0] + x;
+          each((int)cs[id], (int)cs[id + 1]);
+        }
+      }
+    }
+  };
+
+  const bool want = FILL ? a.rowcount[row] > 0 : valid;
+  if (!FILL) {
+    // count pass: fp32 screen, candidates (positions in `sorted`) remembered
+    if (want) {
+      walk([&](int lo, int hi) {
+        for (int t = lo; t < hi; ++t) {
+          const float4 A = sa[t];
+          if (slow || pair_r2<BOXKIND, false>(A.x, A.y, A.z, nxd, nyd, nzd, fb) < cut) {
+            if (nc < (uint32_t)HB_K) my_cand[nc] = t;
+            ++nc;
+          }
+        }
+      });
+    }
+  } else {
+    nc = want ? a.ncand[row] : 0;
+  }
+  if (nc <= (uint32_t)HB_K) {
+    for (uint32_t t = 0; t < nc; ++t) decide(sa[my_cand[t]]);
+  } else {
+    // more candidates than remembered: walk again, deciding in place
+    walk([&](int lo, int hi) {
+      for (int t = lo; t < hi; ++t) {
+        const float4 A = sa[t];
+        if (slow || pair_r2<BOXKIND, false>(A.x, A.y, A.z, nxd, nyd, nzd, fb) < cut)
+          decide(A);
+      }
+    });
+  }
+
+  if (!FILL) {
+    a.rowcount[row] = cnt;
+    a.ncand[row] = nc;
+    long long s = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_warp[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      long long tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      a.blocksum[blk] = tot;
+    }
+  } else if (cnt > 1) {
+    // my bonds by ascending acceptor index (the reference's order); a handful
+    // per row: insertion sort in place
+    const long long end = min(pos + (long long)cnt, a.capacity);
+    for (long long i = pos + 1; i < end; ++i) {
+      const int ka = a.out_acc[i];
+      const double kd = a.out_dist[i];
+      const double kg = a.out_angle ? a.out_angle[i] : 0.0;
+      long long j = i - 1;
+      while (j >= pos && a.out_acc[j] > ka) {
+        a.out_acc[j + 1] = a.out_acc[j];
+        a.out_dist[j + 1] = a.out_dist[j];
+        if (a.out_angle) a.out_angle[j + 1] = a.out_angle[j];
+        --j;
+      }
+      a.out_acc[j + 1] = ka;
+      a.out_dist[j + 1] = kd;
+      if (a.out_angle) a.out_angle[j + 1] = kg;
+    }
+  }
+}
+
 __global__ void hb_edges_kernel(double *edges, double r1) {
   edges[0] = 0.0;
   edges[1] = r1;
@@ -411,14 +660,39 @@ static int launch_hbonds(const float *xyz, int F, int natoms, const int *donors,
   a.ncand = reinterpret_cast<uint32_t *>(ws + L.ncand);
   a.cand = reinterpret_cast<int *>(ws + L.cand);
   a.blocksum = reinterpret_cast<long long *>(ws + L.blocksum);
+  a.cells = nullptr; a.sorted = nullptr;
   a.capacity = capacity;
   a.out_row = out_row; a.out_acc = out_acc;
   a.out_dist = out_dist; a.out_angle = out_angle;
   const dim3 grid((unsigned)L.nblk_x, (unsigned)F);
-  hb_kernel<BOXKIND, false><<<grid, 256, 0, st>>>(a);
-  hb_scan_kernel<<<1, 1024, 0, st>>>(a.blocksum, (long long)L.nblk_x * F, total);
-  hb_kernel<BOXKIND, true><<<grid, 256, 0, st>>>(a);
-  COUNT_LAUNCH(3);
+  // RDFK_DEBUG bit 0: no cell grid, every row against every acceptor (tiled
+  // through shared memory); the results must not depend on it (tests/)
+  int debug_flags = 0;
+  if (const char *dbg = getenv("RDFK_DEBUG")) debug_flags = atoi(dbg);
+  if (debug_flags & 1) {
+    hb_kernel<BOXKIND, false><<<grid, 256, 0, st>>>(a);
+    hb_scan_kernel<<<1, 1024, 0, st>>>(a.blocksum, (long long)L.nblk_x * F, total);
+    hb_kernel<BOXKIND, true><<<grid, 256, 0, st>>>(a);
+    COUNT_LAUNCH(3);
+  } else {
+    uint32_t *cells = reinterpret_cast<uint32_t *>(ws + L.cells);
+    uint32_t *cid = reinterpret_cast<uint32_t *>(ws + L.cid);
+    uint32_t *crank = reinterpret_cast<uint32_t *>(ws + L.crank);
+    float4 *sorted = reinterpret_cast<float4 *>(ws + L.sorted);
+    CUDA_TRY(cudaMemsetAsync(cells, 0, sizeof(uint32_t) * (size_t)HB_NCS * F, st));
+    const dim3 agrid((unsigned)((n_acc + 255) / 256), (unsigned)F);
+    hb_cell_count_kernel<BOXKIND><<<agrid, 256, 0, st>>>(ga, n_acc, L.npa, fparams,
+                                                         cells, cid, crank);
+    scan_kernel<<<F, 1024, 0, st>>>(cells, HB_NCS);
+    hb_cell_scatter_kernel<<<agrid, 256, 0, st>>>(ga, n_acc, L.npa, cells, cid,
+                                                  crank, sorted);
+    a.cells = cells;
+    a.sorted = sorted;
+    hb_cells_kernel<BOXKIND, false><<<grid, 256, 0, st>>>(a);
+    hb_scan_kernel<<<1, 1024, 0, st>>>(a.blocksum, (long long)L.nblk_x * F, total);
+    hb_cells_kernel<BOXKIND, true><<<grid, 256, 0, st>>>(a);
+    COUNT_LAUNCH(6);
+  }
   CUDA_TRY(cudaGetLastError());
   return RDFK_OK;
 }

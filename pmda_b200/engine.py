@@ -1023,7 +1023,8 @@ def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
             pipe = _Pipeline(st, traj, natoms)
             # keep the (frame, donor) row tables of one call bounded (256 MB)
             cap_f = max(1, (256 << 20) // max(56, 56 * n_dh))
-            pipe.batch_frames = max(1, min(pipe.batch_frames, cap_f, 65535))
+            # (and the per-frame cell table of the acceptor grid: 128 KB)
+            pipe.batch_frames = max(1, min(pipe.batch_frames, cap_f, 4096))
             ws = st.get_workspace(be.hbonds_workspace_bytes(
                 pipe.batch_frames, n_dh, n_acc))
             capacity = 0

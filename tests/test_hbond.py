@@ -259,9 +259,22 @@ def test_no_bond_and_no_hydrogen_systems(backend):
 
 # ------------------------------------------------------------------ GPU parity
 def _gpu_run(u, **kw):
+    """runs twice: through the acceptor cell grid and, with RDFK_DEBUG=1,
+    through the brute-force kernel; both must give the same table"""
+    import os
     run_kw = {k: kw.pop(k) for k in ("n_blocks", "n_jobs", "start", "stop",
                                      "step") if k in kw}
-    return HydrogenBondAnalysis(u, **kw).run(**run_kw)
+    old = os.environ.pop("RDFK_DEBUG", None)
+    try:
+        h = HydrogenBondAnalysis(u, **kw).run(**run_kw)
+        os.environ["RDFK_DEBUG"] = "1"
+        brute = HydrogenBondAnalysis(u, **kw).run(**run_kw)
+    finally:
+        os.environ.pop("RDFK_DEBUG", None)
+        if old is not None:
+            os.environ["RDFK_DEBUG"] = old
+    np.testing.assert_array_equal(h.hbonds, brute.hbonds)
+    return h
 
 
 @pytest.mark.gpu
@@ -354,6 +367,37 @@ def test_gpu_far_unwrapped_molecules_and_frame_varying_box():
     h = _gpu_run(u, acceptors_sel=acc, pairs=(don, hyd))
     want = oracle_hbonds(u, don, hyd, acc, range(F))
     assert_same_hbonds(h.hbonds, want)
+
+
+@pytest.mark.gpu
+def test_gpu_cell_grid_shapes():
+    """grids the 27-cell walk has to get right: one periodic axis off, a thin
+    slab (a single cell across), a long box (more cells than the per-axis
+    cap), a box barely wider than two cut-offs (periodic axis falls back to one
+    cell)"""
+    rng = np.random.default_rng(28)
+    for dims, n_mol in (((30.0, 30.0, 0.0, 90, 90, 90), 500),
+                        ((40.0, 40.0, 3.5, 90, 90, 90), 300),
+                        ((150.0, 12.0, 12.0, 90, 90, 90), 600),
+                        ((6.5, 6.5, 6.5, 90, 90, 90), 12),
+                        ((9.5, 30.0, 30.0, 90, 90, 90), 300)):
+        box = tuple(v if v > 0 else 25.0 for v in dims[:3]) + (90, 90, 90)
+        pos, names = synthetic.water_box(3, n_mol, box, rng)
+        u = Universe(pos, list(dims), names=names)
+        don, hyd = water_pairs(u)
+        acc = u.select_atoms("name OW").indices
+        h = _gpu_run(u, acceptors_sel=acc, pairs=(don, hyd))
+        want = oracle_hbonds(u, don, hyd, acc, range(3))
+        assert len(want) > 0, dims
+        assert_same_hbonds(h.hbonds, want)
+    # clustered, no box: the grid spans the extents
+    pos, names = synthetic.water_box(2, 400, (20.0, 20.0, 20.0, 90, 90, 90), rng)
+    pos[:, 600:] += np.float32(35.0)
+    u = Universe(pos, None, names=names)
+    don, hyd = water_pairs(u)
+    acc = u.select_atoms("name OW").indices
+    h = _gpu_run(u, acceptors_sel=acc, pairs=(don, hyd))
+    assert_same_hbonds(h.hbonds, oracle_hbonds(u, don, hyd, acc, range(2)))
 
 
 @pytest.mark.gpu
