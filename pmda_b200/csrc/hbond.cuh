@@ -433,6 +433,46 @@ __global__ __launch_bounds__(256) void hb_cell_count_kernel(
   crank[(size_t)f * np + a] = atomicAdd(cells + (size_t)f * HB_NCS + id, 1u);
 }
 
+// exclusive scan of one frame's cell counts (the cells the frame's grid uses,
+// plus the end marker), one CTA per frame
+__global__ __launch_bounds__(1024) void hb_cell_scan_kernel(
+    uint32_t *__restrict__ cells, const FrameParams *__restrict__ fparams) {
+  int nk[3];
+  hb_grid(fparams[blockIdx.x], nk);
+  const int ncell = nk[0] * nk[1] * nk[2] + 1;
+  uint32_t *c = cells + (size_t)blockIdx.x * HB_NCS;
+  const int tid = threadIdx.x;
+  const int strip = (ncell + 1023) / 1024;
+  const int lo = min(ncell, tid * strip), hi = min(ncell, lo + strip);
+  uint32_t s = 0;
+  for (int i = lo; i < hi; ++i) s += c[i];
+  __shared__ uint32_t wsum[32];
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = wsum[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+      if (tid >= o) w += v;
+    }
+    wsum[tid] = w;
+  }
+  __syncthreads();
+  uint32_t run = incl - s + ((tid >> 5) ? wsum[(tid >> 5) - 1] : 0u);
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t v = c[i];
+    c[i] = run;
+    run += v;
+  }
+}
+
 __global__ __launch_bounds__(256) void hb_cell_scatter_kernel(
     const float *__restrict__ ga, int n, int np,
     const uint32_t *__restrict__ cells, const uint32_t *__restrict__ cid,
@@ -683,7 +723,7 @@ static int launch_hbonds(const float *xyz, int F, int natoms, const int *donors,
     const dim3 agrid((unsigned)((n_acc + 255) / 256), (unsigned)F);
     hb_cell_count_kernel<BOXKIND><<<agrid, 256, 0, st>>>(ga, n_acc, L.npa, fparams,
                                                          cells, cid, crank);
-    scan_kernel<<<F, 1024, 0, st>>>(cells, HB_NCS);
+    hb_cell_scan_kernel<<<F, 1024, 0, st>>>(cells, fparams);
     hb_cell_scatter_kernel<<<agrid, 256, 0, st>>>(ga, n_acc, L.npa, cells, cid,
                                                   crank, sorted);
     a.cells = cells;
