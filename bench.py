@@ -335,7 +335,8 @@ def run_b200(args):
     alg_flop = FLOP_PER_PAIR * frames_all * float(n1) * n2
     achieved = alg_flop / kernel_s / 1e12
     st = engine._state(torch.device("cuda", local_rank))
-    ws = st.workspace[(-st.workspace.data_ptr()) % 256:]
+    ws = st.workspaces[0]          # of the first of the two compute streams
+    ws = ws[(-ws.data_ptr()) % 256:]
     stats = _cabi.rdf_stats(ws, st.compute_stream.cuda_stream)
     hbm_peak = None
     try:

@@ -40,6 +40,8 @@ class Config(object):
     max_batch_frames = int(os.environ.get("PMDA_B200_MAX_BATCH_FRAMES", 2048))
     #: device-resident frame cache budget per GPU (0 disables the cache)
     cache_bytes = int(os.environ.get("PMDA_B200_CACHE_BYTES", 48 << 30))
+    #: compute streams the RDF batches alternate between (1 or 2)
+    compute_streams = int(os.environ.get("PMDA_B200_COMPUTE_STREAMS", 2))
     #: page-lock in-memory trajectories so H2D runs straight from them
     pin_host = os.environ.get("PMDA_B200_PIN_HOST", "1") != "0"
     #: host threads copying frame blocks into the pinned ring
@@ -105,7 +107,9 @@ class _DeviceState(object):
         self.device = device
         self.is_cuda = device.type == "cuda"
         self.lock = threading.Lock()
-        self.workspace = None
+        self.workspaces = [None, None]
+        #: which of the two compute streams (and workspaces) is in use
+        self.cur = 0
         self.pinned = [None, None]
         self.staged = [None, None]
         self.raw_pin = [None, None]      # raw file bytes (DCD blocks)
@@ -115,16 +119,32 @@ class _DeviceState(object):
         if self.is_cuda:
             with torch.cuda.device(device):
                 self.copy_stream = torch.cuda.Stream(device)
-                self.compute_stream = torch.cuda.Stream(device)
+                # two compute streams: consecutive batches of the RDF path
+                # alternate, so the next batch's kernels fill the SMs the
+                # persistent pair kernel's last work items leave idle
+                self.compute_streams = [torch.cuda.Stream(device),
+                                        torch.cuda.Stream(device)]
         else:
-            self.copy_stream = self.compute_stream = None
+            self.copy_stream = None
+            self.compute_streams = [None, None]
+
+    @property
+    def compute_stream(self):
+        return self.compute_streams[self.cur]
+
+    def sync_compute(self):
+        for cs in self.compute_streams:
+            if cs is not None:
+                cs.synchronize()
 
     def get_workspace(self, nbytes):
-        if self.workspace is None or self.workspace.numel() < nbytes:
-            self.workspace = None
-            self.workspace = torch.empty(int(nbytes) + 256, dtype=torch.uint8,
-                                         device=self.device)
-        ws = self.workspace
+        """the workspace of the current compute stream"""
+        have = self.workspaces[self.cur]
+        if have is None or have.numel() < nbytes + 256:
+            self.workspaces[self.cur] = None
+            self.workspaces[self.cur] = torch.empty(
+                int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        ws = self.workspaces[self.cur]
         off = (-ws.data_ptr()) % 256
         return ws[off:off + nbytes]
 
@@ -571,10 +591,15 @@ class _Timer(object):
         else:
             self.t1 = time.time()
 
-    def seconds(self):
+    def seconds(self, after=None):
+        """elapsed seconds; with `after` (the previous batch's timer) only the
+        part that follows that batch's end"""
         if self.st.is_cuda:
             self.e1.synchronize()
-            return self.e0.elapsed_time(self.e1) * 1e-3
+            ms = self.e0.elapsed_time(self.e1)
+            if after is not None:
+                ms = max(0.0, min(ms, after.e1.elapsed_time(self.e1)))
+            return ms * 1e-3
         return self.t1 - self.t0
 
 
@@ -613,16 +638,23 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
             i2 = i1 if same_group else _to_dev_i32(idx2, device)
             n1, n2 = len(idx1), len(idx2)
             pipe = _Pipeline(st, traj, natoms)
-            ws = st.get_workspace(be.rdf_workspace_bytes(
-                pipe.batch_frames, n1, n2, nbins, same_group))
+            ws_bytes = be.rdf_workspace_bytes(pipe.batch_frames, n1, n2, nbins,
+                                              same_group)
             timers = []
+            n_streams = max(1, min(2, Config.compute_streams)) if cuda else 1
+            st.cur = 0
             if cuda:
                 # the zero-fill / uploads above ran on the current stream
-                st.compute_stream.wait_stream(torch.cuda.current_stream(device))
+                for cs in st.compute_streams:
+                    cs.wait_stream(torch.cuda.current_stream(device))
+            n_batch = 0
             for (b, pos0, frames) in segs:
                 done = 0
                 for batch in pipe.batches(frames):
                     B = len(batch)
+                    st.cur = n_batch % n_streams
+                    n_batch += 1
+                    ws = st.get_workspace(ws_bytes)
                     xyz, dims, t_io, slot = pipe.fetch(batch)
                     kinds, box9, vols = _box_rows(dims, B)
                     lo_f = pos0 + done
@@ -646,10 +678,15 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     pipe.mark_compute_done(slot)
                     timers.append((tm, lo_f, B))
                     done += B
+            prev = None
             for tm, lo_f, B in timers:
-                out["compute"][lo_f:lo_f + B] = tm.seconds() / B
+                # batches on alternating streams overlap: a batch is charged
+                # from the end of the previous one (or its own start, if later)
+                out["compute"][lo_f:lo_f + B] = tm.seconds(after=prev) / B
+                prev = tm
             if cuda:
-                st.compute_stream.synchronize()
+                st.sync_compute()
+            st.cur = 0
             out["hist"] = hist
     return out
 
@@ -844,7 +881,7 @@ def _run_sites_part(device, traj, natoms, segs, n_blocks, n_frames, site,
             for tm, lo_f, B in timers:
                 out["compute"][lo_f:lo_f + B] = tm.seconds() / B
             if cuda:
-                st.compute_stream.synchronize()
+                st.sync_compute()
             out["hist"] = count
     return out
 
@@ -952,7 +989,7 @@ def _run_contacts_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
             for tm, lo_f, B in timers:
                 out["compute"][lo_f:lo_f + B] = tm.seconds() / B
             if cuda:
-                st.compute_stream.synchronize()
+                st.sync_compute()
             out["hist"] = series
     return out
 
@@ -1090,7 +1127,7 @@ def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
             for tm, lo_f, B in timers:
                 out["compute"][lo_f:lo_f + B] = tm.seconds() / B
             if cuda:
-                st.compute_stream.synchronize()
+                st.sync_compute()
     return out
 
 

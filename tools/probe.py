@@ -16,7 +16,7 @@ def run(cfg, n_frames, n_atoms=None, reps=3):
         print("cfg%d F=%d N=%dx%d rep%d: wall %.4fs (%.3e pairs/s)  kernel %.4fs (%.3e pairs/s, %.1f frames/s)  count.sum=%d" % (
             cfg, n_frames, len(a["g1"]), len(a["g2"]), rep, dt, pairs/dt, ker, pairs/ker, r.n_frames/ker, r.count.sum()), flush=True)
     st = engine._state(torch.device("cuda", torch.cuda.current_device()))
-    print("  stats:", _cabi.rdf_stats(st.workspace[(-st.workspace.data_ptr()) % 256:], st.compute_stream.cuda_stream))
+    print("  stats:", _cabi.rdf_stats(st.workspaces[0][(-st.workspaces[0].data_ptr()) % 256:], st.compute_stream.cuda_stream))
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), _cabi.device_info(0))
