@@ -9,7 +9,7 @@
 Workload: BASELINE.json configs[1] -- InterRDF all-atom on a synthetic
 100,000-atom orthorhombic box (L = 100 A), nbins = 200, range 0-15 A.  One
 *step* is one ``InterRDF.run()`` over a block of ``--frames-per-step`` frames
-per GPU (default 128 frames = 154 MB of coordinates per GPU, larger than the
+per GPU (default 256 frames = 307 MB of coordinates per GPU, larger than the
 126 MB L2).  Frames are sharded over ranks by the engine; per-rank int64
 histograms are combined by one all-reduce inside ``run()`` (weak scaling:
 per-GPU work is fixed).
@@ -53,21 +53,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=128,
+    ap.add_argument("--frames-per-step", type=int, default=256,
                     help="frames per GPU per step")
     ap.add_argument("--n-atoms", type=int, default=N_ATOMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def synth_positions(n_frames, n_atoms, seed):
-    """uniform ideal gas in [0, L) (synthetic.config2 without the Universe)"""
-    rng = np.random.Generator(np.random.PCG64(seed))
+def synth_positions(n_frames, n_atoms, seed, only=None):
+    """uniform ideal gas in [0, L) (synthetic.config2 without the Universe).
+    Every frame has its own seed, so a rank can generate just the frames of
+    its shard (`only`); the others stay untouched memory it never reads."""
     pos = np.empty((n_frames, n_atoms, 3), dtype=np.float32)
-    for f in range(n_frames):       # frame by frame: bounded temporaries
-        pos[f] = (rng.random((n_atoms, 3)) * BOX_L).astype(np.float32)
     hi = np.nextafter(np.float32(BOX_L), np.float32(0))
-    np.clip(pos, 0, hi, out=pos)
+    for f in (range(n_frames) if only is None else only):
+        rng = np.random.Generator(np.random.PCG64([seed, f]))
+        pos[f] = (rng.random((n_atoms, 3)) * BOX_L).astype(np.float32)
+        np.clip(pos[f], 0, hi, out=pos[f])
     return pos
 
 
@@ -248,7 +250,14 @@ def run_b200(args):
 
     fps = args.frames_per_step
     n_frames = fps * world                       # weak scaling
-    pos = synth_positions(n_frames, args.n_atoms, 20261019 + 2)
+    # the engine gives rank r the r-th of `world` balanced frame blocks
+    from pmda_b200.util import make_balanced_slices
+    blocks = [range(sl.start, sl.stop, sl.step) for sl in
+              make_balanced_slices(n_frames, world, start=0, stop=n_frames,
+                                   step=1)]
+    mine = [f for (_, _, fr) in engine._frame_shards(blocks, world)[rank]
+            for f in fr]
+    pos = synth_positions(n_frames, args.n_atoms, 20261019 + 2, only=mine)
     u = Universe(pos, [BOX_L, BOX_L, BOX_L, 90.0, 90.0, 90.0])
     n1 = n2 = args.n_atoms
     pairs_per_step = float(n_frames) * n1 * n2
