@@ -1483,8 +1483,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
       const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
                 code = (packed >> 24) & 0x7f;
       const float *js = jst + slot * 3 * GJ;
-      n_groups += __popc(qmask);
-      if (all_slow) {
+      if (packed < 0) {   // bit 31: frame on the fp64 path (set when staged)
         // frame not provably safe for fp32: every pair through the fp64 path
         for (int u = 0; u < GJ; ++u) {
           // padding is excluded by index here: the reference arithmetic maps
@@ -1679,12 +1678,15 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
               cp_async16(dst + pl * GJ, src + (size_t)pl * np_j);
               cp_async16(dst + pl * GJ + 4, src + (size_t)pl * np_j + 4);
             }
-            jcode[slot] = pack_group(g, qmask, code);
+            // bit 31 marks a frame on the fp64 path: evaluate() then needs no
+            // per-frame flag in a register of its own
+            jcode[slot] = pack_group(g, qmask, code) | (all_slow ? (int)0x80000000 : 0);
+            n_groups += __popc(qmask);   // (diagnostics: evaluated pairs)
           }
           cp_async_commit_wait_all();
           __syncwarp();
 #pragma unroll 1
-          for (int h = 0; h < nh; ++h) evaluate(h, group_word(h));
+          for (int h = nh - 1; h >= 0; --h) evaluate(h, group_word(h));
         }
       }
       if (!all_slow) drain_small();
@@ -1706,10 +1708,14 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   if (lane == 0) {
     if (tot) atomicAdd(&a.header->stats[0], (unsigned long long)tot);
     if (n_items) atomicAdd(&a.header->stats[2], (unsigned long long)n_items);
-    if (n_groups)
-      atomicAdd(&a.header->stats[3],
-                (unsigned long long)n_groups * (unsigned long long)(32 * GJ));
   }
+  // n_groups: per lane, the (group, quarter) blocks it staged
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    n_groups += __shfl_xor_sync(0xffffffffu, n_groups, o);
+  if (lane == 0 && n_groups)
+    atomicAdd(&a.header->stats[3],
+              (unsigned long long)n_groups * (unsigned long long)(32 * GJ));
 }
 
 // ---------------------------------------------------------------------------
