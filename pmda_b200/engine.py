@@ -162,11 +162,29 @@ def _state(device):
         return st
 
 
+def _evict(st, key=None):
+    """Remove one cached frame block (`key`, or the least recently used one).
+    The block was allocated on torch's current stream but is read by kernels
+    on the compute streams, and the host runs batches ahead of the device:
+    tell the caching allocator not to hand the memory out again before the
+    work queued on those streams has finished."""
+    if key is None:
+        key, entry = st.cache.popitem(last=False)
+    else:
+        entry = st.cache.pop(key)
+    xyz_dev, _, nbytes = entry
+    if st.is_cuda and xyz_dev.is_cuda:
+        for cs in st.compute_streams:
+            xyz_dev.record_stream(cs)
+    st.cache_used -= nbytes
+
+
 def clear_cache():
     """Drop every device-resident frame block (and the staging buffers)."""
     with _states_lock:
         for st in _states.values():
-            st.cache.clear()
+            while st.cache:
+                _evict(st)
             st.cache_used = 0
 
 
@@ -207,7 +225,7 @@ def _purge_dead(st):
         return
     dead = set(_dead_tokens)
     for key in [k for k in st.cache if k[0] in dead]:
-        st.cache_used -= st.cache.pop(key)[2]
+        _evict(st, key)
 
 
 def _fingerprint(pos, dims):
@@ -432,10 +450,9 @@ class _Pipeline(object):
         if cacheable:
             # same block with other contents (edited in-memory trajectory)
             for k in [k for k in st.cache if k[:5] == key[:5]]:
-                st.cache_used -= st.cache.pop(k)[2]
+                _evict(st, k)
             while st.cache and st.cache_used + nbytes > Config.cache_bytes:
-                _, (_, _, freed) = st.cache.popitem(last=False)   # LRU
-                st.cache_used -= freed
+                _evict(st)                                        # LRU
         slot = None
         with torch.cuda.device(st.device):
             # destination: a cache entry of its own, or a rotating buffer
@@ -531,10 +548,9 @@ class _Pipeline(object):
             slot = None
             if cacheable:
                 for k in [k for k in st.cache if k[:5] == key[:5]]:
-                    st.cache_used -= st.cache.pop(k)[2]
+                    _evict(st, k)
                 while st.cache and st.cache_used + nbytes > Config.cache_bytes:
-                    _, (_, _, freed) = st.cache.popitem(last=False)
-                    st.cache_used -= freed
+                    _evict(st)
                 xyz_dev = torch.empty((B, self.natoms, 3), dtype=torch.float32,
                                       device=st.device)
             else:
@@ -660,7 +676,13 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     lo_f = pos0 + done
                     out["vol"][lo_f:lo_f + B] = vols
                     out["io"][lo_f:lo_f + B] = t_io / B
-                    box_d = torch.as_tensor(box9, device=device)
+                    # allocated and filled on the batch's compute stream: the
+                    # host runs batches ahead of the device, and a block freed
+                    # on another stream could be handed out again (and
+                    # overwritten) while this batch's kernels still wait
+                    with (torch.cuda.stream(st.compute_stream) if cuda
+                          else _nullctx()):
+                        box_d = torch.as_tensor(box9, device=device)
                     if cuda:
                         st.compute_stream.wait_stream(
                             torch.cuda.current_stream(device))
@@ -860,7 +882,13 @@ def _run_sites_part(device, traj, natoms, segs, n_blocks, n_frames, site,
                     lo_f = pos0 + done
                     out["vol"][lo_f:lo_f + B] = vols
                     out["io"][lo_f:lo_f + B] = t_io / B
-                    box_d = torch.as_tensor(box9, device=device)
+                    # allocated and filled on the batch's compute stream: the
+                    # host runs batches ahead of the device, and a block freed
+                    # on another stream could be handed out again (and
+                    # overwritten) while this batch's kernels still wait
+                    with (torch.cuda.stream(st.compute_stream) if cuda
+                          else _nullctx()):
+                        box_d = torch.as_tensor(box9, device=device)
                     if cuda:
                         st.compute_stream.wait_stream(
                             torch.cuda.current_stream(device))
@@ -1077,7 +1105,13 @@ def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
                     kinds, box9, _ = _box_rows(dims, B)
                     lo_f = pos0 + done
                     out["io"][lo_f:lo_f + B] = t_io / B
-                    box_d = torch.as_tensor(box9, device=device)
+                    # allocated and filled on the batch's compute stream: the
+                    # host runs batches ahead of the device, and a block freed
+                    # on another stream could be handed out again (and
+                    # overwritten) while this batch's kernels still wait
+                    with (torch.cuda.stream(st.compute_stream) if cuda
+                          else _nullctx()):
+                        box_d = torch.as_tensor(box9, device=device)
                     if cuda:
                         st.compute_stream.wait_stream(
                             torch.cuda.current_stream(device))

@@ -189,6 +189,28 @@ def test_box_changes_every_frame():
     _check_all_modes(u, u.atoms, u.atoms)
 
 
+def test_many_small_batches_with_changing_box():
+    """the host enqueues batches far ahead of the device (frame cache hit, two
+    compute streams): per-batch device buffers such as the box rows must not be
+    recycled while earlier batches still wait to run"""
+    from pmda_b200 import engine
+    rng = np.random.default_rng(117)
+    F, n = 48, 6000
+    Ls = 46.0 + rng.random((F, 3)) * 8.0
+    pos = (rng.random((F, n, 3)) * Ls[:, None, :]).astype(np.float32)
+    dims = np.concatenate([Ls, np.full((F, 3), 90.0)], axis=1).astype(np.float32)
+    u = Universe(pos, dims)
+    want, _, _ = oracle_interrdf(u, u.atoms, u.atoms)
+    old = engine.Config.batch_bytes
+    try:
+        engine.Config.batch_bytes = 3 * n * 12          # 3 frames per batch
+        for rep in range(3):                            # 2nd, 3rd: cache hits
+            got = _gpu(u, u.atoms, u.atoms)
+            np.testing.assert_array_equal(got, want, err_msg="rep %d" % rep)
+    finally:
+        engine.Config.batch_bytes = old
+
+
 def test_exclusion_block_with_sorted_atoms():
     rng = np.random.default_rng(115)
     L = 45.0
