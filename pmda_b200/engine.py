@@ -326,9 +326,12 @@ def _box_rows(dims, n):
     vols = np.zeros(n, dtype=np.float64)
     if dims is None:
         return kinds, box9, vols
-    uniq, inv = np.unique(np.ascontiguousarray(dims), axis=0,
-                          return_inverse=True)
-    inv = inv.reshape(-1)
+    d = np.ascontiguousarray(dims)
+    if len(d) and (d == d[0]).all():        # NVT: one box for the whole batch
+        uniq, inv = d[:1], np.zeros(len(d), dtype=np.intp)
+    else:
+        uniq, inv = np.unique(d, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
     for u, row in enumerate(uniq):
         kind, b = mdamath.classify_box(row)
         vol = float(mdamath.box_volume(row)) if kind != _cabi.BOX_NONE else 0.0
@@ -341,12 +344,13 @@ def _box_rows(dims, n):
 
 def _runs(kinds):
     """consecutive runs of equal box kind -> [(kind, lo, hi)]"""
-    out, lo = [], 0
-    for i in range(1, len(kinds) + 1):
-        if i == len(kinds) or kinds[i] != kinds[lo]:
-            out.append((int(kinds[lo]), lo, i))
-            lo = i
-    return out
+    kinds = np.asarray(kinds)
+    if len(kinds) == 0:
+        return []
+    cuts = np.flatnonzero(kinds[1:] != kinds[:-1]) + 1
+    lo = np.concatenate(([0], cuts))
+    hi = np.concatenate((cuts, [len(kinds)]))
+    return [(int(kinds[a]), int(a), int(b)) for a, b in zip(lo, hi)]
 
 
 def _frame_shards(blocks, n_parts):
