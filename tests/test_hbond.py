@@ -132,6 +132,41 @@ def test_capped_distance_min_cutoff_is_exclusive_max_inclusive():
     assert pairs[:, 1].tolist() == [0, 1, 2, 3]
 
 
+# ------------------------------------------------------------ golden fixtures
+import hashlib                                           # noqa: E402
+import os                                                # noqa: E402
+import sys                                               # noqa: E402
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(_HERE, "golden"))
+import make_hbond_golden as mkhb                         # noqa: E402
+
+HB_GOLD = np.load(os.path.join(_HERE, "golden", "hbond_rows.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(mkhb.CASES))
+def test_oracle_reproduces_golden_hbond_tables(name):
+    rows, digest = mkhb.oracle_rows(name)
+    assert digest == HB_GOLD[name + "__sha256"].tobytes().decode()
+    want = HB_GOLD[name + "__rows"]
+    assert len(want) > 10
+    np.testing.assert_array_equal(rows[:, :5], want[:, :5])
+    np.testing.assert_allclose(rows[:, 5], want[:, 5], rtol=0, atol=ANGLE_TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(mkhb.CASES))
+def test_cuda_path_matches_golden_hbond_tables(name):
+    pos, dims, names, don, hyd, acc, d_a, ang = mkhb.make_inputs(name)
+    assert hashlib.sha256(pos.tobytes()).hexdigest() == \
+        HB_GOLD[name + "__sha256"].tobytes().decode()
+    u = Universe(pos, dims, names=names)
+    h = HydrogenBondAnalysis(u, acceptors_sel=acc, pairs=(don, hyd),
+                             d_a_cutoff=d_a, d_h_a_angle_cutoff=ang).run(
+        n_blocks=min(2, len(pos)))
+    assert_same_hbonds(h.hbonds, HB_GOLD[name + "__rows"])
+
+
 # ------------------------------------------------------------------ host logic
 @pytest.fixture
 def backend():
