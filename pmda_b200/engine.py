@@ -948,10 +948,12 @@ def run_rdf_s_blocks(traj, natoms, site, blocks, nbins, rng, edges, n_jobs):
 
     def make_result(b, flat, vol):
         per_site = np.empty(len(shapes), dtype=object)
-        dense = flat.reshape(total_cells, nbins)
+        # one conversion for all sites; the per-site tensors are disjoint
+        # slices of it
+        dense = flat.reshape(total_cells, nbins).astype(np.float64)
         for s, (n1, n2) in enumerate(shapes):
-            per_site[s] = dense[cell_off[s]:cell_off[s + 1]].astype(
-                np.float64).reshape(n1, n2, nbins)
+            per_site[s] = dense[cell_off[s]:cell_off[s + 1]].reshape(
+                n1, n2, nbins)
         r = np.empty(2, dtype=object)
         r[0] = per_site
         r[1] = np.array(vol, dtype=np.float64)
