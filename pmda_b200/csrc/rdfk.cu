@@ -1094,7 +1094,7 @@ __device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float nxi
   return r2_fast<BOXKIND>(dx, dy, dz, fb);
 }
 
-// Rare path: entry `s` of this lane's queue failed the band test.  Find the
+// Rare path: entry `s` of queue column `col` failed the band test.  Find the
 // group it came from (marks), re-scan that group in the hot loop's order with
 // the hot loop's arithmetic, and bin the pair with the reference arithmetic.
 // Hot-loop order: the quarters of the mask (i-atom r = 0..RI-1), inside the
@@ -1386,7 +1386,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     // band failures are collected in a mask and resolved after the loop.
     auto drain_w = [&](auto width_tag) {
       constexpr int DWL = decltype(width_tag)::value;
-      __syncwarp();   // the group log was written by lane 0
+      __syncwarp();   // log and marks of the last group are visible to all lanes
       // my current column (the pointers rotate one lane per logged group)
       const int col = (lane - nlog) & 31;
       const int n = (int)((qaddr - qw_s) >> 7);
@@ -1507,7 +1507,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         __syncwarp();   // the fp64 loops above diverge per lane
         return;
       }
-      // room for this group (8 pairs per active quarter) in every lane's
+      // room for this group (8 pairs per active quarter) in every queue
       // queue, and for one more entry in the log?
       // (one vote for both conditions: its result is uniform for the compiler,
       // so the branch around the drain needs no convergence barrier)
