@@ -1508,7 +1508,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         return;
       }
       // room for this group (8 pairs per active quarter) in every queue
-      // queue, and for one more entry in the log?
+      // column, and for one more entry in the log?
       // (one vote for both conditions: its result is uniform for the compiler,
       // so the branch around the drain needs no convergence barrier)
       if (__any_sync(0xffffffffu,
