@@ -42,6 +42,8 @@ class Config(object):
     cache_bytes = int(os.environ.get("PMDA_B200_CACHE_BYTES", 48 << 30))
     #: compute streams the RDF batches alternate between (1 or 2)
     compute_streams = int(os.environ.get("PMDA_B200_COMPUTE_STREAMS", 2))
+    #: uncached runs: first batch = 1/head_divisor of the frames (0: off)
+    head_divisor = int(os.environ.get("PMDA_B200_HEAD_DIVISOR", 16))
     #: page-lock in-memory trajectories so H2D runs straight from them
     pin_host = os.environ.get("PMDA_B200_PIN_HOST", "1") != "0"
     #: host threads copying frame blocks into the pinned ring
@@ -404,13 +406,25 @@ class _Pipeline(object):
 
     def batches(self, frames):
         """equal-sized batches of at most ``batch_frames`` frames (a short
-        last batch would leave the persistent kernel's tail under-filled)"""
+        last batch would leave the persistent kernel's tail under-filled),
+        after a short head batch when the frames stream from the host"""
         n = len(frames)
         if n == 0:
             return
-        nb = -(-n // self.batch_frames)
-        size = -(-n // nb)
-        for lo in range(0, n, size):
+        head = 0
+        streaming = self.st.is_cuda and (self.traj_key is None
+                                         or Config.cache_bytes <= 0)
+        if streaming and Config.head_divisor > 0 \
+                and n >= 4 * Config.head_divisor:
+            # frames come from the host every time: a short first batch, whose
+            # upload is the only one no kernel hides (its own kernel tail is
+            # covered by the next batch on the other compute stream)
+            head = n // Config.head_divisor
+            yield frames[:head]
+        rest = n - head
+        nb = -(-rest // self.batch_frames)
+        size = -(-rest // nb)
+        for lo in range(head, n, size):
             yield frames[lo:lo + size]
 
     def fetch(self, frames):
