@@ -1171,7 +1171,9 @@ def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
                                 break
                             want = total + total // 4       # ragged: grow, redo
                         with sctx:
-                            got = tuple(t[:total].cpu().numpy().copy()
+                            # (copy=True: the stand-in CPU backend of the
+                            # tests would otherwise alias the reused buffers)
+                            got = tuple(t[:total].to("cpu", copy=True).numpy()
                                         for t in bufs)
                         out["rows"].append((lo_f + lo, hi - lo) + got)
                     tm.stop()
@@ -1190,29 +1192,21 @@ def run_hbonds_blocks(traj, natoms, spec, blocks, n_jobs):
     ``hydrogens`` (paired absolute atom indices; ``hydrogens`` None = plain
     capped_distance), ``acceptors``, ``max_cutoff``, ``min_cutoff`` (None =
     no lower bound), ``angle_cutoff`` (degrees).  -> per-block tuples whose
-    first element is the float64 ``[n_found, 5]`` array of
-    (position of the frame in the run, D-H row k, acceptor position, distance,
-    angle), ordered by (frame, k, acceptor)."""
+    first element is the column tuple ``(frame, k, acceptor, distance,
+    angle)`` -- position of the frame in the run (int64), D-H row, position
+    in ``acceptors``, float64 distance and angle -- ordered by (frame, k,
+    acceptor)."""
     devices = _backend.devices(n_jobs)
     n_blocks = len(blocks)
     parts, n_frames = _shard_for_this_rank(blocks, devices)
-    n_dh = len(spec["donors"])
+    n_dh = max(len(spec["donors"]), 1)
 
     def fn(device, segs):
         return _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames,
                                 spec)
 
     outs = _run_parts(fn, devices, parts)
-    chunks = []
-    for o in outs:
-        for (pos, nf, row, acc, dist, ang) in o["rows"]:
-            tab = np.empty((len(row), 5), dtype=np.float64)
-            tab[:, 0] = pos + row // max(n_dh, 1)
-            tab[:, 1] = row % max(n_dh, 1)
-            tab[:, 2] = acc
-            tab[:, 3] = dist
-            tab[:, 4] = ang
-            chunks.append((pos, tab))
+    chunks = [c for o in outs for c in o["rows"]]
     extra = np.stack([sum(o["io"] for o in outs),
                       sum(o["compute"] for o in outs)])
     if _dist_world() > 1:
@@ -1221,18 +1215,29 @@ def run_hbonds_blocks(traj, natoms, spec, blocks, n_jobs):
         dist.all_gather_object(gathered, chunks)    # ragged: one exchange
         chunks = [c for part in gathered for c in part]
         extra = _allreduce(torch.from_numpy(extra)).numpy()
-    chunks.sort(key=lambda c: c[0])
-    table = np.concatenate([c[1] for c in chunks]) if chunks \
-        else np.empty((0, 5), dtype=np.float64)
+    chunks.sort(key=lambda c: c[0])                 # by first frame
+    if chunks:
+        row = np.concatenate([c[2] for c in chunks]).astype(np.int64)
+        base = np.concatenate([np.full(len(c[2]), c[0], dtype=np.int64)
+                               for c in chunks])
+        frame = base + row // n_dh
+        k = row % n_dh
+        acc = np.concatenate([c[3] for c in chunks]).astype(np.int64)
+        dist_ = np.concatenate([c[4] for c in chunks])
+        ang = np.concatenate([c[5] for c in chunks])
+    else:
+        frame = k = acc = np.empty(0, dtype=np.int64)
+        dist_ = ang = np.empty(0, dtype=np.float64)
     first = np.min(np.stack([o["first_launch"] for o in outs]), axis=0)
     res, pos = [], 0
-    starts = np.searchsorted(table[:, 0], np.arange(n_frames + 1), side="left")
+    starts = np.searchsorted(frame, np.arange(n_frames + 1), side="left")
     for b, blk in enumerate(blocks):
         n = len(blk)
         t_io = extra[0][pos:pos + n].copy()
         t_c = extra[1][pos:pos + n].copy()
         wait_end = first[b] if np.isfinite(first[b]) else time.time()
-        rows = table[starts[pos]:starts[pos + n]].copy()
-        res.append((rows, t_io, t_c, 0.0, wait_end, np.sum(t_io), np.sum(t_c)))
+        sl = slice(starts[pos], starts[pos + n])
+        cols = (frame[sl], k[sl], acc[sl], dist_[sl], ang[sl])
+        res.append((cols, t_io, t_c, 0.0, wait_end, np.sum(t_io), np.sum(t_c)))
         pos += n
     return res

@@ -107,12 +107,11 @@ class HydrogenBondAnalysis(ParallelAnalysisBase):
             n_jobs)
         per_frame, pos = [], 0
         for blk, el in zip(blocks, raw):
-            rows = el[0]
-            lo = np.searchsorted(rows[:, 0], pos + np.arange(len(blk) + 1))
-            for k in range(len(blk)):
-                r = rows[lo[k]:lo[k + 1]]
-                per_frame.append((donors[r[:, 1].astype(np.intp)],
-                                  hydrogens[r[:, 2].astype(np.intp)]))
+            frame, k, acc = el[0][:3]
+            lo = np.searchsorted(frame, pos + np.arange(len(blk) + 1))
+            for i in range(len(blk)):
+                sl = slice(lo[i], lo[i + 1])
+                per_frame.append((donors[k[sl]], hydrogens[acc[sl]]))
             pos += len(blk)
         return per_frame
 
@@ -164,17 +163,16 @@ class HydrogenBondAnalysis(ParallelAnalysisBase):
         don, hyd, acc = spec["donors"], spec["hydrogens"], spec["acceptors"]
         out, pos = [], 0
         for blk, el in zip(blocks, raw):
-            r = el[0]
+            frame, k, j, dist, ang = el[0]
             frames = np.fromiter(blk, dtype=np.float64, count=len(blk))
-            k = r[:, 1].astype(np.intp)
-            tab = np.empty((len(r), 6), dtype=np.float64)
-            tab[:, 0] = frames[(r[:, 0] - pos).astype(np.intp)] \
-                if len(r) else 0.0
+            tab = np.empty((len(k), 6), dtype=np.float64)
+            if len(k):
+                tab[:, 0] = frames[frame - pos]
             tab[:, 1] = don[k]
             tab[:, 2] = hyd[k]
-            tab[:, 3] = acc[r[:, 2].astype(np.intp)]
-            tab[:, 4] = r[:, 3]
-            tab[:, 5] = r[:, 4]
+            tab[:, 3] = acc[j]
+            tab[:, 4] = dist
+            tab[:, 5] = ang
             out.append((tab,) + tuple(el[1:]))
             pos += len(blk)
         return out
