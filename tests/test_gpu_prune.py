@@ -201,14 +201,22 @@ def test_many_small_batches_with_changing_box():
     dims = np.concatenate([Ls, np.full((F, 3), 90.0)], axis=1).astype(np.float32)
     u = Universe(pos, dims)
     want, _, _ = oracle_interrdf(u, u.atoms, u.atoms)
-    old = engine.Config.batch_bytes
+    old = engine.Config.batch_bytes, engine.Config.cache_bytes
     try:
         engine.Config.batch_bytes = 3 * n * 12          # 3 frames per batch
         for rep in range(3):                            # 2nd, 3rd: cache hits
             got = _gpu(u, u.atoms, u.atoms)
             np.testing.assert_array_equal(got, want, err_msg="rep %d" % rep)
+        # a frame cache of two batches: every batch evicts a block whose
+        # kernels may still be queued
+        engine.clear_cache()
+        engine.Config.cache_bytes = 2 * 3 * n * 12
+        for rep in range(2):
+            got = _gpu(u, u.atoms, u.atoms)
+            np.testing.assert_array_equal(got, want, err_msg="evict %d" % rep)
     finally:
-        engine.Config.batch_bytes = old
+        engine.Config.batch_bytes, engine.Config.cache_bytes = old
+        engine.clear_cache()
 
 
 def test_exclusion_block_with_sorted_atoms():
