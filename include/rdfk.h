@@ -189,6 +189,21 @@ int rdfk_hbonds(const float *xyz, int F, int natoms, const int *donors,
                 size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Frame-cache support (host memory, no CUDA).  The reference re-reads every
+ * frame on every run (pmda/parallel.py:434); a frame block kept resident in
+ * HBM may therefore only be reused if the host data it came from is unchanged.
+ * Returns a 64-bit content hash of EVERY byte of `n_rows` rows of `row_bytes`
+ * bytes lying `row_stride` bytes apart at `base_host` (a strided selection of
+ * frames is hashed in place).  `nthreads` host threads share the work; the
+ * result does not depend on it.  Not cryptographic.
+ * ------------------------------------------------------------------------ */
+unsigned long long rdfk_host_hash64_rows(const void *base_host, size_t n_rows,
+                                         size_t row_bytes,
+                                         long long row_stride,
+                                         unsigned long long seed,
+                                         int nthreads);
+
+/* ------------------------------------------------------------------------
  * Diagnostics / measurement helpers (not on the reference path).
  * ------------------------------------------------------------------------ */
 

@@ -58,6 +58,9 @@ def _declare(L):
         c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
         c_int, c_void_p, c_double, c_double, c_double, c_ll, c_void_p,
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.rdfk_host_hash64_rows.restype = ctypes.c_ulonglong
+    L.rdfk_host_hash64_rows.argtypes = [c_void_p, c_size_t, c_size_t, c_ll,
+                                        ctypes.c_ulonglong, c_int]
     L.rdfk_rdf_stats.restype = c_int
     L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
                                  c_void_p]
@@ -72,6 +75,7 @@ EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
            "rdfk_contacts", "rdfk_unpack_planes",
            "rdfk_hbonds_workspace_bytes", "rdfk_hbonds",
+           "rdfk_host_hash64_rows",
            "rdfk_rdf_stats", "rdfk_launch_count", "rdfk_measure_fp32_peak")
 
 
@@ -181,6 +185,23 @@ def hbonds(xyz, F, natoms, donors, hydrogens, n_dh, acceptors, n_acc, boxkind,
         _ptr(out_dist), _ptr(out_angle), _ptr(total), _ptr(workspace),
         int(workspace.numel() * workspace.element_size()),
         ctypes.c_void_p(int(stream))))
+
+
+def host_hash_rows(arr, seed=0, nthreads=1):
+    """64-bit content hash of every byte of a numpy array whose rows (axis 0)
+    are contiguous inside (any stride between rows).  Releases the GIL."""
+    if arr.ndim == 0 or arr.size == 0:
+        return int(lib().rdfk_host_hash64_rows(None, 0, 0, 0, int(seed), 1))
+    n_rows = arr.shape[0]
+    row = arr[0]
+    if not row.flags.c_contiguous:
+        raise ValueError("rows must be C-contiguous")
+    row_bytes = row.nbytes
+    stride = arr.strides[0] if n_rows > 1 else row_bytes
+    return int(lib().rdfk_host_hash64_rows(
+        ctypes.c_void_p(arr.__array_interface__["data"][0]), int(n_rows),
+        int(row_bytes), int(stride), int(seed) & 0xFFFFFFFFFFFFFFFF,
+        int(nthreads)))
 
 
 def rdf_stats(workspace, stream):

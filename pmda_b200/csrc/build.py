@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",          # every FMA in the kernels is written explicitly
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
     "-I", INCLUDE,
 ]
 
@@ -36,6 +36,7 @@ def needs_build():
         return True
     t = os.path.getmtime(OUT)
     deps = SOURCES + [os.path.join(HERE, "hbond.cuh"),
+                      os.path.join(HERE, "hosthash.inl"),
                       os.path.join(INCLUDE, "rdfk.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -2342,3 +2342,4 @@ extern "C" int rdfk_measure_fp32_peak(double *tflops_host, void *stream) {
 }
 
 #include "hbond.cuh"
+#include "hosthash.inl"

@@ -49,6 +49,12 @@ class Config(object):
     #: host threads copying frame blocks into the pinned ring
     copy_threads = int(os.environ.get("PMDA_B200_COPY_THREADS",
                                       min(8, os.cpu_count() or 1)))
+    #: host threads hashing a cached frame block's host data (every byte; the
+    #: hash runs while the GPU already works on the cached copy)
+    hash_threads = int(os.environ.get(
+        "PMDA_B200_HASH_THREADS",
+        max(1, min(8, (os.cpu_count() or 1) //
+                   max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))))
 
 
 # --------------------------------------------------------------------------
@@ -78,6 +84,7 @@ class CudaBackend(object):
     unpack_planes = staticmethod(_cabi.unpack_planes)
     hbonds_workspace_bytes = staticmethod(_cabi.hbonds_workspace_bytes)
     hbonds = staticmethod(_cabi.hbonds)
+    host_hash_rows = staticmethod(_cabi.host_hash_rows)
 
 
 _backend = CudaBackend()
@@ -174,11 +181,10 @@ def _evict(st, key=None):
         key, entry = st.cache.popitem(last=False)
     else:
         entry = st.cache.pop(key)
-    xyz_dev, _, nbytes = entry
-    if st.is_cuda and xyz_dev.is_cuda:
+    if st.is_cuda and entry.xyz.is_cuda:
         for cs in st.compute_streams:
-            xyz_dev.record_stream(cs)
-    st.cache_used -= nbytes
+            entry.xyz.record_stream(cs)
+    st.cache_used -= entry.nbytes
 
 
 def clear_cache():
@@ -191,9 +197,13 @@ def clear_cache():
 
 
 # A cached frame block is identified by a token that is unique to the live
-# trajectory object (never ``id()``: ids are reused after garbage collection),
-# the frame range, and -- for in-memory trajectories, which the user may
-# modify in place -- a fingerprint of the block's coordinates.
+# trajectory object (never ``id()``: ids are reused after garbage collection)
+# and the frame range.  It is only ever *served* if a 64-bit hash over EVERY
+# byte of the host data it was uploaded from still matches (the reference
+# re-reads each frame on each run, pmda/parallel.py:434: an in-place edit of
+# an in-memory trajectory, or a rewritten file, must show up in the next
+# run()).  Readers whose frames cannot be re-read cheaply (no ``frame_block``
+# / ``raw_block``) are never cached.
 _token_counter = itertools.count(1)
 
 
@@ -230,16 +240,43 @@ def _purge_dead(st):
         _evict(st, key)
 
 
-def _fingerprint(pos, dims):
-    """cheap content check of an in-memory frame block (strided sample)"""
-    flat = pos.reshape(-1)
-    step = max(1, flat.size // 8192)
-    sample = np.ascontiguousarray(flat[::step]).view(np.uint32)
-    fp = int(np.bitwise_xor.reduce(sample)) ^ (int(sample.astype(np.uint64).sum()) << 1)
-    if dims is not None:
-        d = np.ascontiguousarray(dims, dtype=np.float32).view(np.uint32)
-        fp ^= int(d.astype(np.uint64).sum()) << 3
-    return fp
+class _CacheEntry(object):
+    """one frame block resident on a device; ``hash`` = content hash of the
+    host data it was uploaded from (an int, or the Future computing it)"""
+    __slots__ = ("xyz", "nbytes", "hash")
+
+    def __init__(self, xyz, nbytes, hash_):
+        self.xyz, self.nbytes, self.hash = xyz, nbytes, hash_
+
+    def hash_value(self):
+        h = self.hash
+        if not isinstance(h, int):
+            h = self.hash = int(h.result())
+        return h
+
+
+class _StaleFrames(Exception):
+    """a cached frame block did not match the trajectory any more; the stale
+    blocks have been evicted and the part must run again"""
+
+
+_hash_pool = None
+
+
+def _block_hash(arr):
+    """content hash of every byte of a block of frames (rows = frames)"""
+    return _backend.host_hash_rows(arr, 0x706d6461, Config.hash_threads)
+
+
+def _hash_async(arr):
+    """-> Future of :func:`_block_hash`; the native hash releases the GIL, so
+    it runs while this thread keeps launching kernels"""
+    global _hash_pool
+    if _hash_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _hash_pool = ThreadPoolExecutor(max_workers=2,
+                                        thread_name_prefix="pmda-b200-hash")
+    return _hash_pool.submit(_block_hash, arr)
 
 
 _pinned_arrays = {}
@@ -304,17 +341,41 @@ def _copy_frames(dst, src):
         fu.result()
 
 
+_reader_locks = weakref.WeakKeyDictionary()
+_reader_locks_guard = threading.Lock()
+_reader_lock_fallback = threading.Lock()
+
+
+def _reader_lock(traj):
+    """one lock per live reader object (one shared lock for readers that
+    cannot be weakly referenced)"""
+    with _reader_locks_guard:
+        try:
+            lk = _reader_locks.get(traj)
+            if lk is None:
+                lk = _reader_locks[traj] = threading.Lock()
+            return lk
+        except TypeError:
+            return _reader_lock_fallback
+
+
 def _read_frames(traj, frames):
     """-> (positions float32 [B,N,3], dimensions float32 [B,6] | None)"""
     fb = getattr(traj, "frame_block", None)
     if fb is not None:
         return fb(frames)
     pos, dims = [], []
-    for i in frames:                      # any MDAnalysis-like reader
-        ts = traj[i]
-        pos.append(np.array(ts.positions, dtype=np.float32, copy=True))
-        d = getattr(ts, "dimensions", None)
-        dims.append(None if d is None else np.array(d, dtype=np.float32))
+    # Any MDAnalysis-like reader: ``traj[i]`` moves the reader's one file
+    # cursor and refills its one shared ``ts``.  With n_jobs > 1 every device
+    # thread reads from the same reader object, so the seek and the copy out
+    # of ``ts`` are one critical section (the reference avoids the problem by
+    # re-opening the trajectory in every worker, pmda/parallel.py:421).
+    with _reader_lock(traj):
+        for i in frames:
+            ts = traj[i]
+            pos.append(np.array(ts.positions, dtype=np.float32, copy=True))
+            d = getattr(ts, "dimensions", None)
+            dims.append(None if d is None else np.array(d, dtype=np.float32))
     pos = np.stack(pos) if pos else np.zeros((0, 0, 3), np.float32)
     if any(d is None for d in dims):
         return pos, None
@@ -394,12 +455,17 @@ class _Pipeline(object):
         self.h2d_done = [None, None]
         self.compute_done = [None, None]
         _purge_dead(st)
-        self.traj_key = _traj_token(traj)
-        #: in-memory trajectories hand out views: re-reading them is free, so
-        #: the cache entry is validated against the data on every hit
+        #: in-memory / memory-mapped trajectories hand out views: re-reading
+        #: them is free, so a cached block is validated against a hash of the
+        #: current data on every hit.  Other readers are never cached.
         self.cheap_reads = getattr(traj, "frame_block", None) is not None
         #: file formats whose frames can go to the device as they lie on disk
         self.raw = getattr(traj, "raw_block", None) if st.is_cuda else None
+        self.traj_key = _traj_token(traj) \
+            if (self.cheap_reads or self.raw is not None) else None
+        #: cache hits of this run whose host data is still being hashed:
+        #: (key, entry, Future of the current data's hash)
+        self.pending = []
         self.rslot = 0
         self.raw_done = [None, None]
         self.h2d_raw_done = [None, None]
@@ -419,7 +485,7 @@ class _Pipeline(object):
             # frames come from the host every time: a short first batch, whose
             # upload is the only one no kernel hides (its own kernel tail is
             # covered by the next batch on the other compute stream)
-            head = n // Config.head_divisor
+            head = min(n // Config.head_divisor, self.batch_frames)
             yield frames[:head]
         rest = n - head
         nb = -(-rest // self.batch_frames)
@@ -437,18 +503,20 @@ class _Pipeline(object):
         rb = self.raw(frames) if self.raw is not None else None
         if rb is not None:
             return self._fetch_raw(frames, rb, use_cache, t0)
+        hfut = None
         if use_cache:
-            fprint = 0
-            if self.cheap_reads:
-                pos, dims = _read_frames(self.traj, frames)
-                fprint = _fingerprint(pos, dims)
+            pos, dims = _read_frames(self.traj, frames)
             key = (self.traj_key, frames.start, frames.stop, frames.step,
-                   self.natoms, fprint)
+                   self.natoms)
+            # every byte of the host data is hashed -- on a helper thread,
+            # while this one already launches kernels on the cached copy;
+            # verify() compares before any result of the run is used
+            hfut = _hash_async(pos)
             hit = st.cache.get(key)
             if hit is not None:
                 st.cache.move_to_end(key)
-                xyz_dev, dims_c, _ = hit
-                return xyz_dev, dims_c, time.time() - t0, None
+                self.pending.append((key, hit, hfut))
+                return hit.xyz, dims, time.time() - t0, None
         if pos is None:
             pos, dims = _read_frames(self.traj, frames)
         B = len(frames)
@@ -456,21 +524,22 @@ class _Pipeline(object):
             raise ValueError("trajectory frame has %r atoms, expected %d"
                              % (pos.shape[1:], self.natoms))
         nbytes = B * self.frame_bytes
+        cacheable = use_cache and nbytes <= Config.cache_bytes
+        if cacheable:
+            while st.cache and st.cache_used + nbytes > Config.cache_bytes:
+                _evict(st)                                        # LRU
         if not st.is_cuda:
+            # stand-in backends of the tests: same cache logic, host tensors
             host = np.ascontiguousarray(pos)
-            if not host.flags.writeable:        # read-only file mapping
+            if cacheable or not host.flags.writeable:   # own copy / mapping
                 host = np.array(host)
             xyz_dev = torch.from_numpy(host)
+            if cacheable:
+                st.cache[key] = _CacheEntry(xyz_dev, nbytes, hfut)
+                st.cache_used += nbytes
             return xyz_dev, dims, time.time() - t0, None
         cap = self.batch_frames
         shape = (cap, self.natoms, 3)
-        cacheable = use_cache and nbytes <= Config.cache_bytes
-        if cacheable:
-            # same block with other contents (edited in-memory trajectory)
-            for k in [k for k in st.cache if k[:5] == key[:5]]:
-                _evict(st, k)
-            while st.cache and st.cache_used + nbytes > Config.cache_bytes:
-                _evict(st)                                        # LRU
         slot = None
         with torch.cuda.device(st.device):
             # destination: a cache entry of its own, or a rotating buffer
@@ -515,10 +584,25 @@ class _Pipeline(object):
                 self.h2d_done[ps] = ev
             st.compute_stream.wait_event(ev)
         if cacheable:
-            dims_c = None if dims is None else np.array(dims, copy=True)
-            st.cache[key] = (xyz_dev, dims_c, nbytes)
+            st.cache[key] = _CacheEntry(xyz_dev, nbytes, hfut)
             st.cache_used += nbytes
         return xyz_dev, dims, time.time() - t0, slot
+
+    def verify(self):
+        """Compare the hashes of this run's cache hits with the hashes of the
+        data the cached blocks were uploaded from.  Stale blocks are evicted
+        and :class:`_StaleFrames` tells the caller to run the part again (the
+        kernels already ran on the stale copy; their results are dropped)."""
+        pending, self.pending = self.pending, []
+        stale = []
+        for key, entry, fut in pending:
+            if int(fut.result()) != entry.hash_value():
+                stale.append((key, entry))
+        for key, entry in stale:
+            if self.st.cache.get(key) is entry:
+                _evict(self.st, key)
+        if stale:
+            raise _StaleFrames()
 
     def _fetch_raw(self, frames, rb, use_cache, t0):
         """frames as they lie in the file -> pinned ring -> device ->
@@ -528,18 +612,16 @@ class _Pipeline(object):
         B = raw.shape[0]
         nbytes = B * self.frame_bytes
         key = None
+        hfut = None
         if use_cache:
-            flat = raw.reshape(-1)
-            step = max(1, flat.size // 16384)
-            sample = np.ascontiguousarray(flat[::step])
-            fprint = int(sample.astype(np.uint64).sum()) ^ (int(sample[::7].astype(np.uint64).sum()) << 20)
             key = (self.traj_key, frames.start, frames.stop, frames.step,
-                   self.natoms, fprint)
+                   self.natoms)
+            hfut = _hash_async(raw)          # every byte of the file block
             hit = st.cache.get(key)
             if hit is not None:
                 st.cache.move_to_end(key)
-                xyz_dev, dims_c, _ = hit
-                return xyz_dev, dims_c, time.time() - t0, None
+                self.pending.append((key, hit, hfut))
+                return hit.xyz, dims, time.time() - t0, None
         cap = self.batch_frames * fstride
         nraw = B * fstride
         rs = self.rslot
@@ -565,8 +647,6 @@ class _Pipeline(object):
             cacheable = use_cache and nbytes <= Config.cache_bytes
             slot = None
             if cacheable:
-                for k in [k for k in st.cache if k[:5] == key[:5]]:
-                    _evict(st, k)
                 while st.cache and st.cache_used + nbytes > Config.cache_bytes:
                     _evict(st)
                 xyz_dev = torch.empty((B, self.natoms, 3), dtype=torch.float32,
@@ -589,8 +669,7 @@ class _Pipeline(object):
             evu.record(st.compute_stream)
             self.raw_done[rs] = evu
         if cacheable:
-            dims_c = None if dims is None else np.array(dims, copy=True)
-            st.cache[key] = (xyz_dev, dims_c, nbytes)
+            st.cache[key] = _CacheEntry(xyz_dev, nbytes, hfut)
             st.cache_used += nbytes
         return xyz_dev, dims, time.time() - t0, slot
 
@@ -726,6 +805,7 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                 prev = tm
             if cuda:
                 st.sync_compute()
+            pipe.verify()       # cache hits still match the trajectory?
             st.cur = 0
             out["hist"] = hist
     return out
@@ -766,7 +846,18 @@ def _allreduce(t):
     return t
 
 
-def _run_parts(fn, devices, parts):
+def _run_parts(fn_once, devices, parts):
+    def fn(device, part):
+        # a cached frame block turned out stale (the trajectory was edited
+        # since it was uploaded): it has been evicted, run the part again
+        for _ in range(4):
+            try:
+                return fn_once(device, part)
+            except _StaleFrames:
+                continue
+        raise RuntimeError("the trajectory kept changing while run() was "
+                           "reading it")
+
     if len(devices) == 1:
         return [fn(devices[0], parts[0])]
     results = [None] * len(devices)
@@ -928,6 +1019,7 @@ def _run_sites_part(device, traj, natoms, segs, n_blocks, n_frames, site,
                 out["compute"][lo_f:lo_f + B] = tm.seconds() / B
             if cuda:
                 st.sync_compute()
+            pipe.verify()       # cache hits still match the trajectory?
             out["hist"] = count
     return out
 
@@ -1038,6 +1130,7 @@ def _run_contacts_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
                 out["compute"][lo_f:lo_f + B] = tm.seconds() / B
             if cuda:
                 st.sync_compute()
+            pipe.verify()       # cache hits still match the trajectory?
             out["hist"] = series
     return out
 
@@ -1184,6 +1277,7 @@ def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
                 out["compute"][lo_f:lo_f + B] = tm.seconds() / B
             if cuda:
                 st.sync_compute()
+            pipe.verify()       # cache hits still match the trajectory?
     return out
 
 

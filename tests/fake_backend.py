@@ -31,6 +31,12 @@ class OracleBackend(object):
     def rdf_workspace_bytes(F, n1, n2, nbins, same_group):
         return 256
 
+    @staticmethod
+    def host_hash_rows(arr, seed=0, nthreads=1):
+        # host code of the product library (no CUDA involved)
+        from pmda_b200 import _cabi
+        return _cabi.host_hash_rows(arr, seed, nthreads)
+
     def _frame(self, g1, g2, kind, box9, nbins, rng, excl, count):
         lib = c_oracle.lib()
         edges = c_oracle.edges_of(nbins, rng)
