@@ -135,8 +135,22 @@ class Contacts(ParallelAnalysisBase):
                          "r0": np.ascontiguousarray(r0[init], np.float64),
                          "col": col})
             col += len(a) if method == _cabi.CONTACT_DIST else 1
-        return {"refs": refs, "method": method, "radius": radius,
+        spec = {"refs": refs, "method": method, "radius": radius,
                 "beta": beta, "lambda": lam, "width": max(col, 1)}
+        if method == _cabi.CONTACT_DIST:
+            # the user's callable runs on every batch of distances as it
+            # comes off the device (pmda/contacts.py:283-286, per frame)
+            def reduce(dist):
+                y = np.empty((len(dist), len(refs)))
+                for i, ref in enumerate(refs):
+                    lo, n = ref["col"], len(ref["ia"])
+                    for k in range(len(dist)):
+                        y[k, i] = self.fraction_contacts(
+                            dist[k, lo:lo + n], ref["r0"],
+                            **self.fraction_kwargs)
+                return y
+            spec["reduce"] = reduce
+        return spec
 
     def _device_blocks(self, blocks, n_jobs):
         spec = self._spec()
@@ -151,11 +165,7 @@ class Contacts(ParallelAnalysisBase):
             for i, ref in enumerate(spec["refs"]):
                 n = len(ref["ia"])
                 if spec["method"] == _cabi.CONTACT_DIST:
-                    lo = ref["col"]
-                    for k in range(len(blk)):
-                        y[k, i + 1] = self.fraction_contacts(
-                            series[k, lo:lo + n], ref["r0"],
-                            **self.fraction_kwargs)
+                    y[:, i + 1] = series[:, i]
                 else:
                     with np.errstate(divide='ignore', invalid='ignore'):
                         y[:, i + 1] = series[:, ref["col"]] / n

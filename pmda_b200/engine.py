@@ -1087,9 +1087,17 @@ def _run_contacts_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
         cuda = st.is_cuda
         ctx = torch.cuda.device(device) if cuda else _nullctx()
         with ctx:
-            # one row per frame of the run (frames of other devices stay 0)
-            series = torch.zeros((n_frames, width), dtype=torch.float64,
+            # one row per frame of the run (frames of other devices stay 0).
+            # User callables (CONTACT_DIST) get their distances batch by
+            # batch: only the callable's value per (frame, reference) is kept,
+            # never the [n_frames, n_pairs] distance table of the whole run.
+            emit = spec["method"] == _cabi.CONTACT_DIST
+            reduce_fn = spec.get("reduce") if emit else None
+            keep = len(spec["refs"]) if reduce_fn is not None else width
+            series = torch.zeros((n_frames, keep), dtype=torch.float64,
                                  device=device)
+            series_host = np.zeros((n_frames, keep)) \
+                if reduce_fn is not None else None
             refs = []
             for ref in spec["refs"]:
                 refs.append((_to_dev_i32(ref["ia"], device),
@@ -1098,7 +1106,7 @@ def _run_contacts_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
                                              device=device),
                              len(ref["ia"]), ref["col"]))
             pipe = _Pipeline(st, traj, natoms)
-            if spec["method"] == _cabi.CONTACT_DIST:
+            if emit:
                 # keep batches of emitted distances bounded (256 MB)
                 cap = max(1, (256 << 20) // max(8, 8 * width))
                 pipe.batch_frames = max(1, min(pipe.batch_frames, cap))
@@ -1117,13 +1125,25 @@ def _run_contacts_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
                     tm = _Timer(st)
                     tm.start()
                     stream = st.compute_stream.cuda_stream if cuda else 0
+                    sctx = torch.cuda.stream(st.compute_stream) if cuda \
+                        else _nullctx()
+                    if reduce_fn is not None:
+                        with sctx:
+                            dest = torch.empty((B, width), dtype=torch.float64,
+                                               device=device)
+                    else:
+                        dest = series[lo_f:lo_f + B]
                     for (ia, ib, r0, npairs, col) in refs:
                         be.contacts(xyz, B, natoms, ia, ib, r0, npairs,
                                     spec["method"], spec["radius"],
                                     spec["beta"], spec["lambda"],
-                                    series[lo_f:lo_f + B, col:], width, stream)
+                                    dest[:, col:], width, stream)
                     tm.stop()
                     pipe.mark_compute_done(slot)
+                    if reduce_fn is not None:
+                        with sctx:
+                            dist_host = dest.to("cpu").numpy()  # synchronises
+                        series_host[lo_f:lo_f + B] = reduce_fn(dist_host)
                     timers.append((tm, lo_f, B))
                     done += B
             for tm, lo_f, B in timers:
@@ -1131,6 +1151,8 @@ def _run_contacts_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
             if cuda:
                 st.sync_compute()
             pipe.verify()       # cache hits still match the trajectory?
+            if series_host is not None:
+                series = torch.as_tensor(series_host, device=device)
             out["hist"] = series
     return out
 
@@ -1151,8 +1173,10 @@ def run_contacts_blocks(traj, natoms, spec, blocks, n_jobs):
                                   n_frames, spec)
 
     outs = _run_parts(fn, devices, parts)
-    series = _combine(outs, devices[0], n_frames, spec["width"],
-                      torch.float64)
+    keep = len(spec["refs"]) if (spec["method"] == _cabi.CONTACT_DIST and
+                                 spec.get("reduce") is not None) \
+        else spec["width"]
+    series = _combine(outs, devices[0], n_frames, keep, torch.float64)
     series = _allreduce(series)          # every frame was computed by one rank
     extra = np.stack([sum(o["vol"] for o in outs),
                       sum(o["io"] for o in outs),

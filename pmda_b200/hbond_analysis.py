@@ -144,7 +144,15 @@ class HydrogenBondAnalysis(ParallelAnalysisBase):
         self.timesteps = (self.frames * dt) + t0
         self._acceptors_ids = _as_indices(self._universe, self.acceptors_sel,
                                           "acceptors_sel")
-        self._donors_ids, self._hydrogens_ids = self._get_dh_pairs()
+        # The reference pairs donors with hydrogens on a Universe it has just
+        # built and moved to frame 0 (pmda/hbond_analysis.py:398-408): always
+        # frame 0, never the frame the caller's reader happens to stand on.
+        # With update_selections the pairs are re-derived for every frame of
+        # the run (_device_blocks), so this search would be thrown away.
+        if self._repairs_every_frame():
+            self._donors_ids = self._hydrogens_ids = None
+        else:
+            self._donors_ids, self._hydrogens_ids = self._get_dh_pairs(frame=0)
 
     def _spec(self, donors, hydrogens):
         return {"donors": donors, "hydrogens": hydrogens,
@@ -177,9 +185,12 @@ class HydrogenBondAnalysis(ParallelAnalysisBase):
             pos += len(blk)
         return out
 
+    def _repairs_every_frame(self):
+        return (self.update_selections and self._pairs is None
+                and self.donors_sel is not None)
+
     def _device_blocks(self, blocks, n_jobs):
-        repair = (self.update_selections and self._pairs is None
-                  and self.donors_sel is not None)
+        repair = self._repairs_every_frame()
         if not repair:
             return self._rows(self._spec(self._donors_ids,
                                          self._hydrogens_ids), blocks, n_jobs)

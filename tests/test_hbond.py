@@ -257,6 +257,19 @@ def test_update_selections_follows_changing_pairs(backend):
                                             1.2, box=ts0.dimensions)
     want = oracle_hbonds(u, d[pairs[:, 0]], hy[pairs[:, 1]], acc, range(4))
     np.testing.assert_array_equal(h2.hbonds, want)
+    # ... wherever the caller's reader stands: the reference pairs on a fresh
+    # Universe at frame 0 (pmda/hbond_analysis.py:398-408)
+    u.trajectory[3]
+    calls = backend.calls
+    h3 = HydrogenBondAnalysis(u, don_sel, hyd_sel, "name OW",
+                              update_selections=False).run()
+    np.testing.assert_array_equal(h3.hbonds, want)
+    # with update_selections the pairs of every frame come from one search
+    # over the run: no extra pairing search in _prepare
+    per_run = backend.calls - calls
+    calls = backend.calls
+    HydrogenBondAnalysis(u, don_sel, hyd_sel, "name OW").run()
+    assert backend.calls - calls <= per_run + 4
 
 
 def test_start_stop_step_and_single_frame(backend):
