@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RDFK_VERSION 120
+#define RDFK_VERSION 130
 
 #define RDFK_OK 0
 #define RDFK_EINVAL -1    /* bad argument                                   */
@@ -52,6 +52,19 @@ extern "C" {
 
 int rdfk_version(void);
 const char *rdfk_last_error(void);
+
+/* Cross-check switches for the test suite; 0 (the default) in production.
+ * bit 0: no bounding-box pruning (every group pair is evaluated; hydrogen
+ * bonds: no acceptor cell grid), bit 1: no one-shift-per-group arithmetic,
+ * bit 2: no Euclidean refinement of the triclinic box test.  Results never
+ * depend on the flags, throughput does.  An explicit call on purpose -- not an
+ * environment variable a production job could inherit.  Process-wide; returns
+ * the previous flags.                                                        */
+int rdfk_set_debug_flags(int flags);
+
+/* 1 when the library was built with -DRDFK_CHECK (device-side guard rails on
+ * the pair kernel's per-warp queue / log bounds; see rdfk_rdf_stats), else 0 */
+int rdfk_build_has_checks(void);
 
 /* sm count, compute capability and opt-in shared memory of `device`.       */
 int rdfk_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
@@ -207,11 +220,18 @@ unsigned long long rdfk_host_hash64_rows(const void *base_host, size_t n_rows,
  * Diagnostics / measurement helpers (not on the reference path).
  * ------------------------------------------------------------------------ */
 
-/* counters of the last rdfk_rdf_hist call that used `workspace`:
- * out_host[0] = pairs sent to the fp64 re-check, out_host[1] = frames that
- * ran entirely on the fp64 path, out_host[2] = (frame, 128-atom cluster) work
- * items executed, out_host[3] = pairs evaluated by the pair kernel (after the
- * bounding-box pruning).  Synchronises `stream`.                             */
+/* counters kept in `workspace` by rdfk_rdf_hist; out_host holds 8 values.
+ * Of the last call: [0] pairs sent to the fp64 re-check, [1] frames that ran
+ * entirely on the fp64 path, [2] (frame, 128-atom cluster) work items
+ * executed, [3] pairs evaluated by the pair kernel (after the bounding-box
+ * pruning).  Cumulative since the first call on this workspace: [4] atoms
+ * that lay outside the primary triclinic cell and were wrapped into it (the
+ * _triclinic_pbc step of distance_array, whose operation order is the one
+ * part of the arithmetic restated without a pinned reference: see DESIGN.md),
+ * [5] frames that held such atoms, [6] internal consistency violations (a
+ * queue entry whose pair could not be found again -- always counted -- and,
+ * in RDFK_CHECK builds, queue / log bound violations; must be 0), [7] code of
+ * the first violation.  Synchronises `stream`.                               */
 int rdfk_rdf_stats(const void *workspace, unsigned long long *out_host,
                    void *stream);
 

@@ -28,6 +28,10 @@ def _declare(L):
     L.rdfk_version.argtypes = []
     L.rdfk_last_error.restype = ctypes.c_char_p
     L.rdfk_last_error.argtypes = []
+    L.rdfk_set_debug_flags.restype = c_int
+    L.rdfk_set_debug_flags.argtypes = [c_int]
+    L.rdfk_build_has_checks.restype = c_int
+    L.rdfk_build_has_checks.argtypes = []
     L.rdfk_device_info.restype = c_int
     L.rdfk_device_info.argtypes = [c_int, ctypes.POINTER(c_int),
                                    ctypes.POINTER(c_int), ctypes.POINTER(c_int),
@@ -71,7 +75,8 @@ def _declare(L):
 
 
 #: every symbol include/rdfk.h declares
-EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_device_info",
+EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_set_debug_flags",
+           "rdfk_build_has_checks", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
            "rdfk_contacts", "rdfk_unpack_planes",
            "rdfk_hbonds_workspace_bytes", "rdfk_hbonds",
@@ -205,11 +210,22 @@ def host_hash_rows(arr, seed=0, nthreads=1):
 
 
 def rdf_stats(workspace, stream):
-    out = (ctypes.c_ulonglong * 4)()
+    out = (ctypes.c_ulonglong * 8)()
     check(lib().rdfk_rdf_stats(_ptr(workspace), out,
                                ctypes.c_void_p(int(stream))))
     return {"slow_pairs": int(out[0]), "all_slow_frames": int(out[1]),
-            "tile_items": int(out[2]), "tile_pairs": int(out[3])}
+            "tile_items": int(out[2]), "tile_pairs": int(out[3]),
+            "wrapped_atoms": int(out[4]), "wrapped_frames": int(out[5]),
+            "violations": int(out[6]), "first_violation": int(out[7])}
+
+
+def set_debug_flags(flags):
+    """cross-check switches of the test suite (rdfk.h); returns the old ones"""
+    return int(lib().rdfk_set_debug_flags(int(flags)))
+
+
+def build_has_checks():
+    return bool(lib().rdfk_build_has_checks())
 
 
 def launch_count():

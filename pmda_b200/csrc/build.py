@@ -14,6 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 INCLUDE = os.path.join(ROOT, "include")
 SOURCES = [os.path.join(HERE, "rdfk.cu")]
 OUT = os.path.join(HERE, "librdfk.so")
+#: the same sources with -DRDFK_CHECK (device-side guard rails on the pair
+#: kernel's queue / log bounds); one GPU test runs the parity cases through it
+OUT_CHECK = os.path.join(HERE, "librdfk_check.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -31,10 +34,11 @@ def _nvcc():
     return "nvcc"
 
 
-def needs_build():
-    if not os.path.exists(OUT):
+def needs_build(out=None):
+    out = out or OUT
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     deps = SOURCES + [os.path.join(HERE, "hbond.cuh"),
                       os.path.join(HERE, "hosthash.inl"),
                       os.path.join(INCLUDE, "rdfk.h"), os.path.abspath(__file__)]
@@ -50,6 +54,13 @@ def build(force=False, verbose=False, out=None, defines=()):
         + ["-D" + d for d in defines] + SOURCES + ["-o", out or OUT]
     subprocess.check_call(cmd)
     return out or OUT
+
+
+def build_check(force=False):
+    """the RDFK_CHECK variant next to the release library"""
+    if not force and not needs_build(OUT_CHECK):
+        return OUT_CHECK
+    return build(out=OUT_CHECK, defines=("RDFK_CHECK",))
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@
 //   hb_scan_kernel           exclusive scan of the per-CTA totals (+ grand total)
 //   hb_cells_kernel<true>    rows written at their offsets: replays the
 //                            remembered candidates (a row with more walks again)
-//   (RDFK_DEBUG bit 0: hb_kernel instead -- no grid, every acceptor, tiled
+//   (rdfk_set_debug_flags bit 0: hb_kernel instead -- no grid, every acceptor, tiled
 //   through shared memory; same results)
 // The result is ordered by (frame, D-H row, acceptor): the row-major order of
 // the reference's brute-force `np.where(mask)`.
@@ -49,7 +49,7 @@ static HbLayout hb_layout(int F, int n_dh, int n_acc) {
   w.header = off;
   off = align_up(off + sizeof(WsHeader), 256);
   w.extents = off;
-  off = align_up(off + sizeof(int) * 6 * (size_t)F, 256);
+  off = align_up(off + sizeof(int) * EXT * (size_t)F, 256);
   w.fparams = off;
   off = align_up(off + sizeof(FrameParams) * (size_t)F, 256);
   w.tables = off;
@@ -672,7 +672,7 @@ static int launch_hbonds(const float *xyz, int F, int natoms, const int *donors,
   float *gh = reinterpret_cast<float *>(ws + L.gh);
   float *ga = reinterpret_cast<float *>(ws + L.ga);
 
-  init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(header, extents, F, 0);
+  init_ws_kernel<<<(F * EXT + 255) / 256 + 1, 256, 0, st>>>(header, extents, F, 0);
   hb_edges_kernel<<<1, 1, 0, st>>>(edges, max_cutoff);
   stage_kernel<BOXKIND><<<dim3((L.npd + 255) / 256, F), 256, 0, st>>>(
       xyz, natoms, donors, n_dh, L.npd, box, gd, extents);
@@ -686,7 +686,7 @@ static int launch_hbonds(const float *xyz, int F, int natoms, const int *donors,
   // debug flag 2: bounds of the per-pair minimum image only (no shifted variant)
   params_kernel<<<(F + 127) / 128, 128, 0, st>>>(BOXKIND, box, extents, hp, 2, F,
                                                  fparams);
-  tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header);
+  tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header, extents);
   COUNT_LAUNCH(hydrogens ? 7 : 6);
 
   HbArgs a;
@@ -705,10 +705,9 @@ static int launch_hbonds(const float *xyz, int F, int natoms, const int *donors,
   a.out_row = out_row; a.out_acc = out_acc;
   a.out_dist = out_dist; a.out_angle = out_angle;
   const dim3 grid((unsigned)L.nblk_x, (unsigned)F);
-  // RDFK_DEBUG bit 0: no cell grid, every row against every acceptor (tiled
+  // rdfk_set_debug_flags bit 0: no cell grid, every row against every acceptor (tiled
   // through shared memory); the results must not depend on it (tests/)
-  int debug_flags = 0;
-  if (const char *dbg = getenv("RDFK_DEBUG")) debug_flags = atoi(dbg);
+  const int debug_flags = __atomic_load_n(&g_debug_flags, __ATOMIC_RELAXED);
   if (debug_flags & 1) {
     hb_kernel<BOXKIND, false><<<grid, 256, 0, st>>>(a);
     hb_scan_kernel<<<1, 1024, 0, st>>>(a.blocksum, (long long)L.nblk_x * F, total);

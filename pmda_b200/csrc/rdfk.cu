@@ -61,6 +61,11 @@ static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
 #define COUNT_LAUNCH(n) __atomic_fetch_add(&g_launches, (unsigned long long)(n), __ATOMIC_RELAXED)
 
+// cross-check switches of the test suite (rdfk_set_debug_flags); 0 in
+// production.  Deliberately NOT an environment variable: a stray export must
+// not be able to switch off the pruning of a production run.
+static int g_debug_flags = 0;
+
 static int set_err(int code, const char *fmt, const char *a = "",
                    const char *b = "") {
   snprintf(g_err, sizeof(g_err), fmt, a, b);
@@ -123,11 +128,43 @@ struct HistParams {
   int nbins;
 };
 
+// stats: [0] pairs sent to the fp64 re-check, [1] frames entirely on the fp64
+// path, [2] work items, [3] evaluated pairs (all of the last call); cumulative
+// over the life of the workspace: [4] atoms the triclinic wrap moved, [5]
+// frames with such atoms, [6] RDFK_CHECK violations, [7] code of the first one
 struct WsHeader {
-  unsigned long long stats[4];  // slow pairs, all-slow frames, items, pairs
+  unsigned long long stats[8];
+  unsigned long long magic;   // header has been initialised (cumulative stats)
   int work_counter;
   float r2_cut[2];  // fp32 r2 >= r2_cut[t] => reference distance > r1 for sure
-  int pad[5];       // pad[0]: triclinic refinement off (RDFK_DEBUG bit 2)
+  int pad[5];       // pad[0]: triclinic refinement off (debug flag bit 2)
+};
+constexpr unsigned long long WS_MAGIC = 0x7264666b5f777331ull;   // "rdfk_ws1"
+constexpr int EXT = 8;   // ints per frame in `extents`: min xyz, max xyz (as
+                         // ordered ints), atoms moved by the wrap, unused
+
+// Debug-build guard rails (compute-sanitizer stands in for none of this on
+// pools where it is closed): with -DRDFK_CHECK the pair kernel verifies the
+// bounds of its per-warp queue / log / marks and that resolve_entry() finds
+// the pair behind every queue entry; violations are counted in stats[6],
+// the first code is kept in stats[7].  Release builds compile this away.
+#ifdef RDFK_CHECK
+#define RDFK_CHECK_THAT(header, cond, code)                                   \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      atomicAdd(&(header)->stats[6], 1ull);                                   \
+      atomicCAS(&(header)->stats[7], 0ull, (unsigned long long)(code));       \
+    }                                                                         \
+  } while (0)
+#else
+#define RDFK_CHECK_THAT(header, cond, code) do { } while (0)
+#endif
+enum {
+  CHK_QUEUE_OVERFLOW = 1,   // a queue column grew beyond QS rows
+  CHK_LOG_OVERFLOW = 2,     // more than LOGMAX groups logged between drains
+  CHK_RESOLVE_MISS = 3,     // resolve_entry() did not find the entry's pair
+                            // (counted in release builds too)
+  CHK_STAGE_SLOT = 5,       // staged group slot / index out of range
 };
 
 struct WsLayout {
@@ -153,7 +190,7 @@ static WsLayout ws_layout(int F, int n1, int n2, int nbins, int same_group) {
   w.header = off;
   off = align_up(off + sizeof(WsHeader), 256);
   w.extents = off;
-  off = align_up(off + sizeof(int) * 6 * (size_t)F, 256);
+  off = align_up(off + sizeof(int) * EXT * (size_t)F, 256);
   w.fparams = off;
   off = align_up(off + sizeof(FrameParams) * (size_t)F, 256);
   w.tables = off;
@@ -361,10 +398,17 @@ __global__ void init_ws_kernel(WsHeader *h, int *extents, int F,
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0) {
     h->stats[0] = h->stats[1] = h->stats[2] = h->stats[3] = 0ull;
+    if (h->magic != WS_MAGIC) {   // first call on this workspace
+      h->stats[4] = h->stats[5] = h->stats[6] = h->stats[7] = 0ull;
+      h->magic = WS_MAGIC;
+    }
     h->work_counter = 0;
     h->pad[0] = no_refine;
   }
-  if (t < F * 6) extents[t] = (t % 6 < 3) ? INT_MAX : INT_MIN;
+  if (t < F * EXT) {
+    const int k = t % EXT;
+    extents[t] = k < 3 ? INT_MAX : (k < 6 ? INT_MIN : 0);
+  }
 }
 
 // One thread per (frame, padded atom slot).  Replaces `ag.positions`
@@ -379,6 +423,7 @@ __global__ __launch_bounds__(256) void stage_kernel(
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   float x = __int_as_float(0x7fc00000), y = x, z = x;  // NaN padding
   const bool valid = a < n;
+  int n_moved = 0;
   if (valid) {
     const int src = idx ? idx[a] : a;
     const float *p = xyz + ((size_t)f * natoms + src) * 3;
@@ -415,7 +460,14 @@ __global__ __launch_bounds__(256) void stage_kernel(
         moved = true;
       }
       if (moved) { x = (float)c0; y = (float)c1; z = (float)c2; }
+      n_moved = moved ? 1 : 0;
     }
+  }
+  if (BOXKIND == RDFK_BOX_TRI) {
+    // atoms outside the primary cell (the branch whose operation order is
+    // not pinned against MDAnalysis): counted per frame for rdfk_rdf_stats
+    const int m = __syncthreads_count(n_moved);
+    if (threadIdx.x == 0 && m) atomicAdd(extents + f * EXT + 6, m);
   }
   if (a < npad) {
     float *o = out + (size_t)f * 3 * npad;
@@ -453,7 +505,7 @@ __global__ __launch_bounds__(256) void stage_kernel(
       lo = fminf(lo, s_mn[w][k]);
       hi = fmaxf(hi, s_mx[w][k]);
     }
-    int *e = extents + f * 6;
+    int *e = extents + f * EXT;
     if (lo < big) atomicMin(e + k, float_to_ordered(lo));
     if (hi > -big) atomicMax(e + 3 + k, float_to_ordered(hi));
   }
@@ -468,7 +520,7 @@ __global__ void params_kernel(int boxkind, const float *__restrict__ box,
   if (f >= F) return;
   FrameParams *fp = fparams + f;
   {
-    const int *e = extents + f * 6;
+    const int *e = extents + f * EXT;
     double X[3], A[3], lo3[3];
     bool slow = false, finite = true;
     for (int k = 0; k < 3; ++k) {
@@ -637,7 +689,8 @@ __global__ void params_kernel(int boxkind, const float *__restrict__ box,
 // valid), so the pair kernel can keep them in shared memory.
 __global__ __launch_bounds__(256) void tables_kernel(
     HistParams hp, int F, FrameParams *__restrict__ fparams,
-    float2 *__restrict__ tables, WsHeader *__restrict__ header) {
+    float2 *__restrict__ tables, WsHeader *__restrict__ header,
+    const int *__restrict__ extents) {
   __shared__ float s_max[2][8];
   float m0 = 0.f, m1 = 0.f;
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
@@ -705,6 +758,11 @@ __global__ __launch_bounds__(256) void tables_kernel(
       if (fp->fl[k] > 0.f && !(rs < 0.4999 * (double)fp->fl[k])) ok = false;
     fp->shift_ok = ok ? 1 : 0;
     if (fp->all_slow) atomicAdd(&header->stats[1], 1ull);
+    const int moved = extents[f * EXT + 6];
+    if (moved > 0) {
+      atomicAdd(&header->stats[4], (unsigned long long)moved);
+      atomicAdd(&header->stats[5], 1ull);
+    }
   }
 }
 
@@ -1138,7 +1196,7 @@ __device__ __noinline__ int resolve_entry(
       }
     }
   }
-  return -1;  // unreachable: the entry was produced by one of these pairs
+  return -2;  // unreachable: the entry was produced by one of these pairs
 }
 
 template <int BOXKIND, bool GLOBAL_HIST>
@@ -1451,6 +1509,13 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                                                 fp, &s_hp);
           ++n_slow;
           if (kk >= 0) count_bin(kk);
+          // never drop a pair silently (release builds too; rare path):
+          // rdfk_rdf_stats reports it and the engine raises
+          if (kk == -2) {
+            atomicAdd(&a.header->stats[6], 1ull);
+            atomicCAS(&a.header->stats[7], 0ull,
+                      (unsigned long long)CHK_RESOLVE_MISS);
+          }
         }
         // lanes leave the loop at different times and are not guaranteed to
         // reconverge by themselves; the log and marks they read are reused
@@ -1515,6 +1580,10 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                      (nlog == LOGMAX) |
                          (qaddr > qw_s + (QS - GJ * __popc(qmask)) * 128 + 127)))
         drain();
+      RDFK_CHECK_THAT(a.header, nlog >= 0 && nlog < LOGMAX, CHK_LOG_OVERFLOW);
+      RDFK_CHECK_THAT(a.header,
+                      (int)((qaddr - qw_s) >> 7) + GJ * __popc(qmask) <= QS,
+                      CHK_QUEUE_OVERFLOW);
       // (shared-window addresses: a generic store recomputes the window base)
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(glog_s + 4u * nlog), "r"(packed));
       asm volatile("st.shared.u8 [%0], %1;" ::"r"(mark_s + 32u * nlog +
@@ -1591,6 +1660,8 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
                    cut);
         }
       }
+      RDFK_CHECK_THAT(a.header, (int)((qaddr - qw_s) >> 7) <= QS,
+                      CHK_QUEUE_OVERFLOW);
       // hand my queue column to the next lane: every column collects the hits
       // of many different i-atoms, so the columns fill evenly and the rows the
       // drain walks are denser
@@ -1671,6 +1742,8 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
           __syncwarp();   // every lane is done with the previous staging round
           if (gpass) {
             const int slot = __popc(gmask & lt_mask);
+            RDFK_CHECK_THAT(a.header, slot >= 0 && slot < NSTAGE && g >= 0 &&
+                                          g < a.ngrp_j, CHK_STAGE_SLOT);
             float *dst = jst + slot * 3 * GJ;
             const float *src = gj_f + (size_t)g * GJ;
 #pragma unroll
@@ -1949,6 +2022,16 @@ static int check_device(int *sm_count) {
 }
 
 extern "C" int rdfk_version(void) { return RDFK_VERSION; }
+extern "C" int rdfk_set_debug_flags(int flags) {
+  return __atomic_exchange_n(&g_debug_flags, flags, __ATOMIC_RELAXED);
+}
+extern "C" int rdfk_build_has_checks(void) {
+#ifdef RDFK_CHECK
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" const char *rdfk_last_error(void) { return g_err; }
 
 extern "C" int rdfk_device_info(int device, int *sm_count, int *cc_major,
@@ -2021,12 +2104,11 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   uint32_t *lrank = reinterpret_cast<uint32_t *>(ws + L.lrank);
   uint32_t *cells = reinterpret_cast<uint32_t *>(ws + L.cells);
 
-  // RDFK_DEBUG: bit 0 = no pruning (every group is evaluated), bit 1 = no
-  // shifted variant, bit 2 = no Euclidean refinement of the triclinic box
-  // test.  Results must not depend on any of them (tests/).
-  int debug_flags = 0;
-  if (const char *dbg = getenv("RDFK_DEBUG")) debug_flags = atoi(dbg);
-  init_ws_kernel<<<(F * 6 + 255) / 256 + 1, 256, 0, st>>>(
+  // rdfk_set_debug_flags: bit 0 = no pruning (every group is evaluated), bit
+  // 1 = no shifted variant, bit 2 = no Euclidean refinement of the triclinic
+  // box test.  Results must not depend on any of them (tests/).
+  const int debug_flags = __atomic_load_n(&g_debug_flags, __ATOMIC_RELAXED);
+  init_ws_kernel<<<(F * EXT + 255) / 256 + 1, 256, 0, st>>>(
       header, extents, F, (debug_flags & 4) ? 1 : 0);
   COUNT_LAUNCH(same_group ? 4 : 5);  // init + stage(s) + params + tables
   stage_kernel<BOXKIND><<<dim3((L.np1 + 255) / 256, F), 256, 0, st>>>(
@@ -2036,7 +2118,7 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
         xyz, natoms, idx2, n2, L.np2, box, g2, extents);
   params_kernel<<<(F + 127) / 128, 128, 0, st>>>(BOXKIND, box, extents, hp,
                                                  debug_flags, F, fparams);
-  tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header);
+  tables_kernel<<<1, 256, 0, st>>>(hp, F, fparams, tables, header, extents);
 
   float *qbb1 = reinterpret_cast<float *>(ws + L.qbb1);
   float *qbb2 = reinterpret_cast<float *>(ws + L.qbb2);
@@ -2303,7 +2385,7 @@ extern "C" int rdfk_rdf_stats(const void *workspace,
   if (!workspace || !out_host)
     return set_err(RDFK_EINVAL, "null pointer argument%s%s");
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(cudaMemcpyAsync(out_host, workspace, 4 * sizeof(unsigned long long),
+  CUDA_TRY(cudaMemcpyAsync(out_host, workspace, 8 * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return RDFK_OK;

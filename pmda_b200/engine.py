@@ -23,6 +23,7 @@ import itertools
 import os
 import threading
 import time
+import warnings
 import weakref
 from collections import OrderedDict
 
@@ -123,8 +124,10 @@ class _DeviceState(object):
         self.staged = [None, None]
         self.raw_pin = [None, None]      # raw file bytes (DCD blocks)
         self.raw_dev = [None, None]
-        self.cache = OrderedDict()   # key -> (xyz_dev, nbytes)
+        self.cache = OrderedDict()   # key -> _CacheEntry
         self.cache_used = 0
+        #: wrapped-frames counter of each workspace at the last report
+        self.wrapped_seen = {}
         if self.is_cuda:
             with torch.cuda.device(device):
                 self.copy_stream = torch.cuda.Stream(device)
@@ -153,6 +156,15 @@ class _DeviceState(object):
             self.workspaces[self.cur] = None
             self.workspaces[self.cur] = torch.empty(
                 int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            # librdfk recognises its own header by a magic word: make sure a
+            # recycled allocation does not carry an old one
+            # (on the stream the kernels of this workspace run on)
+            if self.is_cuda:
+                with torch.cuda.stream(self.compute_stream):
+                    self.workspaces[self.cur][:512].zero_()
+            else:
+                self.workspaces[self.cur][:512].zero_()
+            self.wrapped_seen.pop(self.cur, None)
         ws = self.workspaces[self.cur]
         off = (-ws.data_ptr()) % 256
         return ws[off:off + nbytes]
@@ -797,6 +809,19 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     pipe.mark_compute_done(slot)
                     timers.append((tm, lo_f, B))
                     done += B
+            # the counters librdfk keeps in the first 64 bytes of a workspace
+            # (rdfk.h, rdfk_rdf_stats), fetched behind the last kernels
+            stats_host = []
+            if cuda:
+                for k in range(n_streams):
+                    ws_k = st.workspaces[k]
+                    if ws_k is None or n_batch <= k:
+                        continue
+                    off = (-ws_k.data_ptr()) % 256
+                    with torch.cuda.stream(st.compute_streams[k]):
+                        stats_host.append(
+                            ws_k[off:off + 64].view(torch.int64).to(
+                                "cpu", non_blocking=True))
             prev = None
             for tm, lo_f, B in timers:
                 # batches on alternating streams overlap: a batch is charged
@@ -808,7 +833,32 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
             pipe.verify()       # cache hits still match the trajectory?
             st.cur = 0
             out["hist"] = hist
+            _check_stats(st, stats_host)
     return out
+
+
+def _check_stats(st, stats_host):
+    """act on librdfk's workspace counters after a run (rdfk.h): internal
+    violations are fatal; atoms outside the primary triclinic cell are
+    reported once per growth of the counter"""
+    for k, t in enumerate(stats_host):
+        s = t.numpy()
+        if s[6]:
+            raise _cabi.RdfkError(
+                "librdfk internal check failed %d time(s), first code %d: the "
+                "histogram of this run is not trustworthy" % (s[6], s[7]))
+        seen = st.wrapped_seen.get(k, 0)
+        if s[5] > seen:
+            st.wrapped_seen[k] = int(s[5])
+            warnings.warn(
+                "%d frame(s) held atoms outside the primary triclinic unit "
+                "cell (%d atoms so far); they were wrapped into it before the "
+                "distance search like MDAnalysis' distance_array does, but "
+                "the operation order of that wrap is the one part of the "
+                "arithmetic that is not pinned against MDAnalysis (DESIGN.md "
+                "section 6): wrap the trajectory beforehand to be on the "
+                "pinned branch" % (s[5] - seen, s[4]), RuntimeWarning,
+                stacklevel=4)
 
 
 class _nullctx(object):

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = _cabi.lib()
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.rdfk_version() == 120
+    assert lib.rdfk_version() == 130
 
 
 def test_argument_validation_needs_no_gpu():
@@ -95,3 +95,28 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "liboracle" not in src, f
+
+
+def test_debug_switches_are_an_explicit_call_not_an_environment_variable():
+    """the release library read RDFK_DEBUG with getenv on every
+    call, so a stray export could switch off pruning in production."""
+    csrc = os.path.join(ROOT, "pmda_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh", ".inl")):
+            src = open(os.path.join(csrc, f)).read()
+            assert "getenv" not in src, f
+    blob = open(_cabi.LIB_PATH, "rb").read()
+    assert b"RDFK_DEBUG" not in blob
+    assert _cabi.set_debug_flags(5) == 0
+    assert _cabi.set_debug_flags(0) == 5
+    assert not _cabi.build_has_checks()
+
+
+def test_check_build_exports_the_same_symbols():
+    from pmda_b200.csrc import build as b
+    path = b.build_check()
+    lib = ctypes.CDLL(path)
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    lib.rdfk_build_has_checks.restype = ctypes.c_int
+    assert lib.rdfk_build_has_checks() == 1

@@ -3,7 +3,7 @@
 The oracle is O(N1 N2) on the host, so at these sizes it checks *row
 subsamples* of the pair matrix (a few hundred g1 atoms against the full g2);
 the full matrix is covered by size-independent properties: the pruned/shifted
-kernel must give the integers of its own brute-force mode (RDFK_DEBUG=3: every
+kernel must give the integers of its own brute-force mode (debug flags 3: every
 group pair evaluated, per-pair minimum image only), counts of a symmetric
 selection are even off the self pairs, block/step decompositions agree, and an
 ideal gas has g(r) = 1 within Poisson noise."""
@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from pmda_b200 import synthetic
+from pmda_b200 import _cabi, synthetic
 from pmda_b200.rdf import InterRDF, InterRDF_s
 
 from helpers import oracle_interrdf, oracle_interrdf_s
@@ -21,15 +21,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(g1, g2, nbins, rng, debug=None, **kw):
-    old = os.environ.pop("RDFK_DEBUG", None)
+    old = _cabi.set_debug_flags(0 if debug is None else int(debug))
     try:
-        if debug is not None:
-            os.environ["RDFK_DEBUG"] = str(debug)
         return InterRDF(g1, g2, nbins=nbins, range=rng).run(**kw)
     finally:
-        os.environ.pop("RDFK_DEBUG", None)
-        if old is not None:
-            os.environ["RDFK_DEBUG"] = old
+        _cabi.set_debug_flags(old)
 
 
 def _rows(u, g, n, seed):

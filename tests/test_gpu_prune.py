@@ -1,6 +1,6 @@
 """GPU parity for the sorted / pruned pair kernel: everything the spatial sort,
 the box tests and the one-shift-per-group fast path could get wrong must still
-give the oracle's integers.  RDFK_DEBUG (bit 0: no pruning, bit 1: no shifted
+give the oracle's integers.  rdfk_set_debug_flags (bit 0: no pruning, bit 1: no shifted
 variant, bit 2: no Euclidean refinement of the triclinic box test) is read by
 librdfk on every call; results must not depend on it."""
 import os
@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from pmda_b200 import synthetic
+from pmda_b200 import _cabi, synthetic
 from pmda_b200.rdf import InterRDF
 from pmda_b200.universe import Universe
 
@@ -18,24 +18,20 @@ pytestmark = pytest.mark.gpu
 
 
 def _gpu(u, g1, g2, nbins=75, rng=(0.0, 15.0), excl=None, debug=None):
-    old = os.environ.pop("RDFK_DEBUG", None)
+    old = _cabi.set_debug_flags(0 if debug is None else int(debug))
     try:
-        if debug is not None:
-            os.environ["RDFK_DEBUG"] = str(debug)
         r = InterRDF(g1, g2, nbins=nbins, range=rng, exclusion_block=excl)
         r.run()
         return r.count.copy()
     finally:
-        os.environ.pop("RDFK_DEBUG", None)
-        if old is not None:
-            os.environ["RDFK_DEBUG"] = old
+        _cabi.set_debug_flags(old)
 
 
 def _check_all_modes(u, g1, g2, nbins=75, rng=(0.0, 15.0), excl=None):
     want, _, _ = oracle_interrdf(u, g1, g2, nbins, rng, excl)
     for debug in (None, 1, 2, 3, 4, 6):
         got = _gpu(u, g1, g2, nbins, rng, excl, debug)
-        np.testing.assert_array_equal(got, want, err_msg="RDFK_DEBUG=%r" % debug)
+        np.testing.assert_array_equal(got, want, err_msg="debug flags %r" % debug)
     return want
 
 

@@ -307,20 +307,18 @@ def test_no_bond_and_no_hydrogen_systems(backend):
 
 # ------------------------------------------------------------------ GPU parity
 def _gpu_run(u, **kw):
-    """runs twice: through the acceptor cell grid and, with RDFK_DEBUG=1,
+    """runs twice: through the acceptor cell grid and, with debug flag 1,
     through the brute-force kernel; both must give the same table"""
-    import os
+    from pmda_b200 import _cabi
     run_kw = {k: kw.pop(k) for k in ("n_blocks", "n_jobs", "start", "stop",
                                      "step") if k in kw}
-    old = os.environ.pop("RDFK_DEBUG", None)
+    old = _cabi.set_debug_flags(0)
     try:
         h = HydrogenBondAnalysis(u, **kw).run(**run_kw)
-        os.environ["RDFK_DEBUG"] = "1"
+        _cabi.set_debug_flags(1)
         brute = HydrogenBondAnalysis(u, **kw).run(**run_kw)
     finally:
-        os.environ.pop("RDFK_DEBUG", None)
-        if old is not None:
-            os.environ["RDFK_DEBUG"] = old
+        _cabi.set_debug_flags(old)
     np.testing.assert_array_equal(h.hbonds, brute.hbonds)
     return h
 
