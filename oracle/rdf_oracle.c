@@ -24,6 +24,31 @@
  *                MDAnalysis, so these are anchored on
  *                known-answer tests we wrote ourselves (tests/test_kat.py).
  *
+ * Upstream release each restated function follows (recollection of the
+ * published sources; nothing of MDAnalysis is available offline to check):
+ *   minimum_image, _calc_distance_array, _calc_distance_array_ortho,
+ *   _calc_distance_array_triclinic, minimum_image_triclinic (27-image search,
+ *   strict '<', FLT_MAX start)
+ *       calc_distances.h as shipped from MDAnalysis 0.20 through 2.x (the
+ *       1.0.x line pmda's setup.py:51 asks for is inside that range; the
+ *       functions did not change across it).
+ *   _triclinic_pbc (oracle_triclinic_wrap)
+ *       the double-precision "lower bound / upper bound" variant of 1.0.x-2.x
+ *       (wrap along c, then b, then a; coordinates already inside the cell
+ *       untouched).  Releases up to 0.19 wrapped in float with
+ *       floor(coord / box) per axis; the two differ for out-of-cell input, and
+ *       the exact operation order of the newer one is NOT trusted either.
+ *   _bruteforce_capped (d <= max_cutoff on the distance_array result)
+ *       lib/distances.py 0.19 through 2.x.
+ *   numpy.histogram's uniform-bin rule: numpy >= 1.15 (checked live).
+ * tools/pin_against_mdanalysis.py is the one-command way to turn "recollection"
+ * into "pinned": where MDAnalysis imports it recomputes every golden case and
+ * the out-of-cell / on-edge / angle cases with the real library, diffs them
+ * against this file and writes tests/golden/mdanalysis_pinned.npz, which
+ * tests/test_pinning.py then enforces for the oracle and the CUDA path.  The
+ * product counts frames that took the wrap branch (rdfk_rdf_stats [4], [5])
+ * and the engine warns about them.
+ *
  * Call sites in the reference that this file follows:
  *   pmda/rdf.py:120-137  InterRDF._single_frame   -> oracle_rdf_frame
  *   pmda/rdf.py:292-309  InterRDF_s._single_frame -> oracle_rdf_s_frame
