@@ -152,3 +152,81 @@ def config5(n_frames=10_000, n_atoms=1_000_000, n_g1=1000, seed_extra=0):
 
 
 CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}
+
+
+# -- the same five configurations, generated frame by frame ------------------
+# Every frame has its own seed, so each rank of a multi-GPU run can generate
+# just the frames of its shard (bench.py): `only` = the frame numbers to fill;
+# the other frames stay uninitialised memory that the rank never reads.
+def _frame_rng(cfg, f):
+    return np.random.Generator(np.random.PCG64([BASE_SEED, cfg, 1 + int(f)]))
+
+
+def _static_rng(cfg):
+    return np.random.Generator(np.random.PCG64([BASE_SEED, cfg, 0]))
+
+
+def sharded_config(cfg, n_frames, only=None, n_atoms=None):
+    """-> (Universe, kwargs) like ``CONFIGS[cfg]`` but frame-seeded.  The
+    static part (lattice sites, site selections, slab membership) comes from a
+    per-config seed and is identical on every rank."""
+    frames = range(n_frames) if only is None else only
+    srng = _static_rng(cfg)
+    if cfg == 1:
+        n, L = n_atoms or 3000, 44.78
+        m = int(np.ceil(n ** (1.0 / 3.0)))
+        g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"),
+                     axis=-1).reshape(-1, 3)
+        sites = (g[srng.permutation(len(g))[:n]] + 0.5) * (L / m)
+        pos = np.empty((n_frames, n, 3), dtype=np.float32)
+        for f in frames:
+            p = np.mod(sites + _frame_rng(cfg, f).normal(0.0, 0.5, (n, 3)), L)
+            pos[f] = _clamp_ortho(p.astype(np.float32), [L, L, L])
+        u = Universe(pos, [L, L, L, 90, 90, 90])
+        return u, dict(g1=u.atoms, g2=u.atoms, nbins=75, range=(0.0, 15.0))
+    if cfg == 2:
+        n, L = n_atoms or 100_000, 100.0
+        pos = np.empty((n_frames, n, 3), dtype=np.float32)
+        for f in frames:
+            pos[f] = uniform_ortho(1, n, [L, L, L], _frame_rng(cfg, f))[0]
+        u = Universe(pos, [L, L, L, 90, 90, 90])
+        return u, dict(g1=u.atoms, g2=u.atoms, nbins=200, range=(0.0, 15.0))
+    if cfg == 3:
+        n, L, n_sites, n_near = n_atoms or 50_000, 79.4, 64, 256
+        base = uniform_ortho(1, n, [L, L, L], srng)[0].astype(np.float64)
+        pos = np.empty((n_frames, n, 3), dtype=np.float32)
+        for f in frames:
+            p = np.mod(base + _frame_rng(cfg, f).normal(0.0, 0.3, (n, 3)), L)
+            pos[f] = _clamp_ortho(p.astype(np.float32), [L, L, L])
+        u = Universe(pos, [L, L, L, 90, 90, 90])
+        ions = srng.choice(n, n_sites, replace=False)
+        ags = []
+        for ion in ions:          # the 256 atoms nearest to the ion's site
+            d = base - base[ion]
+            d -= L * np.round(d / L)
+            order = np.argsort(np.einsum("ij,ij->i", d, d))
+            ags.append([u.atoms[[ion]], u.atoms[np.sort(order[1:n_near + 1])]])
+        return u, dict(ags=ags, nbins=75, range=(0.0, 15.0), density=True)
+    if cfg == 4:
+        n, dims = n_atoms or 250_000, [152.3, 152.3, 152.3, 60.0, 60.0, 90.0]
+        pos = np.empty((n_frames, n, 3), dtype=np.float32)
+        for f in frames:
+            pos[f] = uniform_triclinic(1, n, dims, _frame_rng(cfg, f))[0]
+        u = Universe(pos, dims)
+        return u, dict(g1=u.atoms, g2=u.atoms, nbins=75, range=(0.0, 15.0))
+    if cfg == 5:
+        n, Ls, n_g1 = n_atoms or 1_000_000, [316.2, 316.2, 100.0], 1000
+        n_slab = n // 2
+        centre = np.where(srng.random(n_slab) < 0.5, 35.0, 65.0)
+        pos = np.empty((n_frames, n, 3), dtype=np.float32)
+        for f in frames:
+            rng = _frame_rng(cfg, f)
+            p = uniform_ortho(1, n, Ls, rng)[0]
+            z = centre + rng.normal(0.0, 8.0, n_slab)
+            p[:n_slab, 2] = np.mod(z, Ls[2]).astype(np.float32)
+            pos[f] = _clamp_ortho(p, Ls)
+        u = Universe(pos, Ls + [90, 90, 90])
+        g1 = u.atoms[np.sort(srng.choice(n_slab, min(n_g1, n_slab),
+                                         replace=False))]
+        return u, dict(g1=g1, g2=u.atoms, nbins=75, range=(0.0, 15.0))
+    raise ValueError("no BASELINE config %r" % (cfg,))

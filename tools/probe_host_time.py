@@ -1,0 +1,54 @@
+"""Where does run() spend host time on the small configurations?  cProfile of
+repeated run()s (BASELINE configs[0] and [2]), resident and end to end."""
+import cProfile
+import io
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from pmda_b200 import engine, synthetic  # noqa: E402
+from pmda_b200.rdf import InterRDF, InterRDF_s  # noqa: E402
+
+
+def main():
+    which = [int(a) for a in sys.argv[1:]] or [1, 3]
+    for cfg in which:
+        nf = {1: 100, 3: 400}[cfg]
+        u, kw = synthetic.sharded_config(cfg, nf)
+        if cfg == 3:
+            make = lambda: InterRDF_s(u, kw["ags"], nbins=kw["nbins"],
+                                      range=kw["range"])
+        else:
+            make = lambda: InterRDF(kw["g1"], kw["g2"], nbins=kw["nbins"],
+                                    range=kw["range"])
+        for cache in (64 << 30, 0):
+            engine.Config.cache_bytes = cache
+            engine.clear_cache()
+            for _ in range(5):
+                make().run()
+            torch.cuda.synchronize()
+            reps = 50
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r = make().run()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            print("cfg%d cache=%s: run() %.3f ms, kernels %.3f ms, %d frames/s"
+                  % (cfg, bool(cache), dt * 1e3,
+                     1e3 * float(r.timing.compute.sum()), nf / dt), flush=True)
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(reps):
+                make().run()
+            pr.disable()
+            s = io.StringIO()
+            pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
+            print("\n".join(l for l in s.getvalue().splitlines()
+                            if l.strip())[:6000], flush=True)
+
+
+if __name__ == "__main__":
+    main()
