@@ -502,16 +502,17 @@ def run_config(job, cfg, reps=4, warm=2, cpu_shape=False):
     return out
 
 
-def cpu_pmda_shape(u, kw, n_frames=12):
+def cpu_pmda_shape(u, kw):
     """configs[0] as BASELINE.json asks for it on the CPU: n_jobs=4, one
     process per block, per-frame distance_array + mask + np.histogram
-    (oracle/pmda_cpu.py) -- on a bounded 12-frame sample"""
+    (oracle/pmda_cpu.py) -- on a bounded sample of 3 frames per worker"""
     from oracle import pmda_cpu
-    pos = u.trajectory.positions[:n_frames]
     dims = u.trajectory.dimensions[0]
     ix = kw["g1"].indices
     out = {}
     for jobs in sorted({4, min(host_cores(), 16)}):
+        n_frames = min(3 * jobs, len(u.trajectory.positions))
+        pos = u.trajectory.positions[:n_frames]
         r = pmda_cpu.interrdf_process_per_block(
             pos, dims, ix, ix, kw["nbins"], kw["range"], n_jobs=jobs)
         out["n_jobs_%d" % jobs] = {

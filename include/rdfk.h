@@ -119,6 +119,21 @@ int rdfk_rdf_sites(const float *xyz, int F, int natoms, const int *idxA,
                    double r0, double r1, int nbins, const double *edges,
                    unsigned int *count, void *stream);
 
+/* InterRDF_s epilogue (pmda/rdf.py:311-334) for the counts of n_blocks frame
+ * blocks, count[b][i], i < n = cells * nbins:
+ *   count_f64[b][i] = (double) count[b][i]        the float64 tensors the
+ *                                                  reference returns per block
+ *   total[i]        = sum_b count[b][i]           np.sum(self._results[:, 0])
+ *   rdf[i]          = total[i] / den[i % nbins]   den = density*vol*n_frames or
+ *                                                  vol*n_frames, computed by the
+ *                                                  caller in the reference's
+ *                                                  operation order
+ * Any of the three outputs may be NULL.  The division is one IEEE double
+ * division per element, as in numpy: same bits.                            */
+int rdfk_sites_finish(const unsigned int *count, int n_blocks, long long n,
+                      int nbins, const double *den, double *count_f64,
+                      double *total, double *rdf, void *stream);
+
 /* ------------------------------------------------------------------------
  * Contacts frame kernel (the sibling analysis on the same
  * distance arithmetic).  Replaces, for F frames at once, the body of
@@ -215,6 +230,17 @@ unsigned long long rdfk_host_hash64_rows(const void *base_host, size_t n_rows,
                                          long long row_stride,
                                          unsigned long long seed,
                                          int nthreads);
+
+/* Host-side gather of the atoms an analysis references (all pointers HOST
+ * memory, no CUDA): dst[f][k][0..2] = src[f][idx[k]][0..2] for f < n_frames,
+ * k < n_idx, float32 triples, source frames `frame_stride` bytes apart.  This
+ * is the `ag.positions` gather of pmda/rdf.py:296-301, done before the upload
+ * so that only referenced atoms cross PCIe; `nthreads` host threads share the
+ * frames.                                                                    */
+int rdfk_host_gather_rows(const void *src_host, size_t n_frames,
+                          long long frame_stride, size_t natoms,
+                          const int *idx_host, size_t n_idx, float *dst_host,
+                          int nthreads);
 
 /* ------------------------------------------------------------------------
  * Diagnostics / measurement helpers (not on the reference path).

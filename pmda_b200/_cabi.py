@@ -48,6 +48,9 @@ def _declare(L):
         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
         c_void_p, c_int, c_ll, c_int, c_void_p, c_double, c_double, c_int,
         c_void_p, c_void_p, c_void_p]
+    L.rdfk_sites_finish.restype = c_int
+    L.rdfk_sites_finish.argtypes = [c_void_p, c_int, c_ll, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]
     L.rdfk_contacts.restype = c_int
     L.rdfk_contacts.argtypes = [
         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -65,6 +68,9 @@ def _declare(L):
     L.rdfk_host_hash64_rows.restype = ctypes.c_ulonglong
     L.rdfk_host_hash64_rows.argtypes = [c_void_p, c_size_t, c_size_t, c_ll,
                                         ctypes.c_ulonglong, c_int]
+    L.rdfk_host_gather_rows.restype = c_int
+    L.rdfk_host_gather_rows.argtypes = [c_void_p, c_size_t, c_ll, c_size_t,
+                                        c_void_p, c_size_t, c_void_p, c_int]
     L.rdfk_rdf_stats.restype = c_int
     L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
                                  c_void_p]
@@ -78,9 +84,10 @@ def _declare(L):
 EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_set_debug_flags",
            "rdfk_build_has_checks", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
+           "rdfk_sites_finish",
            "rdfk_contacts", "rdfk_unpack_planes",
            "rdfk_hbonds_workspace_bytes", "rdfk_hbonds",
-           "rdfk_host_hash64_rows",
+           "rdfk_host_hash64_rows", "rdfk_host_gather_rows",
            "rdfk_rdf_stats", "rdfk_launch_count", "rdfk_measure_fp32_peak")
 
 
@@ -155,6 +162,16 @@ def rdf_sites(xyz, F, natoms, idx_a, idx_b, off_a, off_b, cell_off, n_sites,
         _ptr(count), ctypes.c_void_p(int(stream))))
 
 
+def sites_finish(count, n_blocks, n, nbins, den, count_f64, total, rdf,
+                 stream):
+    """rdfk_sites_finish: uint32 counts -> float64 per-block tensors, their
+    sum and the rdf (any output may be None)"""
+    check(lib().rdfk_sites_finish(
+        _ptr(count), int(n_blocks), int(n), int(nbins), _ptr(den),
+        _ptr(count_f64), _ptr(total), _ptr(rdf),
+        ctypes.c_void_p(int(stream))))
+
+
 CONTACT_HARD, CONTACT_RADIUS, CONTACT_SOFT, CONTACT_DIST = 0, 1, 2, 3
 
 
@@ -207,6 +224,27 @@ def host_hash_rows(arr, seed=0, nthreads=1):
         ctypes.c_void_p(arr.__array_interface__["data"][0]), int(n_rows),
         int(row_bytes), int(stride), int(seed) & 0xFFFFFFFFFFFFFFFF,
         int(nthreads)))
+
+
+def host_gather_rows(src, idx, dst, nthreads=1):
+    """dst[f, k] = src[f, idx[k]] for float32 [F, N, 3] `src` whose frames
+    are C-contiguous inside (any stride between frames), int32 `idx`,
+    C-contiguous float32 [F, len(idx), 3] `dst`.  Releases the GIL."""
+    import numpy as np
+    if src.dtype != np.float32 or dst.dtype != np.float32 or \
+            idx.dtype != np.int32 or not idx.flags.c_contiguous or \
+            not dst.flags.c_contiguous or src.ndim != 3 or src.shape[2] != 3 \
+            or (len(src) and not src[0].flags.c_contiguous) or \
+            dst.shape != (len(src), len(idx), 3):
+        raise ValueError("host_gather_rows: bad array layout")
+    if len(src) == 0 or len(idx) == 0:
+        return
+    stride = src.strides[0] if len(src) > 1 else src[0].nbytes
+    check(lib().rdfk_host_gather_rows(
+        ctypes.c_void_p(src.__array_interface__["data"][0]), len(src),
+        int(stride), int(src.shape[1]),
+        ctypes.c_void_p(idx.__array_interface__["data"][0]), len(idx),
+        ctypes.c_void_p(dst.__array_interface__["data"][0]), int(nthreads)))
 
 
 def rdf_stats(workspace, stream):

@@ -1012,7 +1012,8 @@ struct PairArgs {
   int ncl_i, ncl_j, ngrp_j;
   int symmetric;      // gi == gj: circulant half of the cluster matrix
   int swapped;        // i side is the reference's g2 (`conf`), j side its g1
-  int total_items;    // F * ncl_i
+  int total_items;    // F * ncl_i * nsplit
+  int nsplit;         // work items per (frame, i-cluster): slices of the j side
   const FrameParams *fparams;
   const float2 *tables;   // [F][2][nbins + 1]
   HistParams hp;
@@ -1033,18 +1034,25 @@ struct PairArgs {
 // the last drain and every lane marks its queue length at each group start,
 // so the rare band failure re-scans one group (resolve_entry).
 // ---------------------------------------------------------------------------
-constexpr int QS = 64;        // queue slots per lane
+constexpr int QS_MAX = 64;    // queue slots per lane (fail mask is 64 bits)
+// tunables of the triclinic instantiation (A/B builds: -DRDFK_...=n)
+#ifndef RDFK_TPB_TRI
+#define RDFK_TPB_TRI 256      // threads per CTA
+#endif
+#ifndef RDFK_IAT_SMEM_TRI
+#define RDFK_IAT_SMEM_TRI 1   // i-atoms in shared memory instead of registers
+#endif
+#ifndef RDFK_QS_TRI
+#define RDFK_QS_TRI ((RDFK_IAT_SMEM_TRI && RDFK_TPB_TRI == 256) ? 56 : 64)
+#endif
 constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
 constexpr int NSTAGE = 32;    // staged j-groups per warp (one test round)
 constexpr int PAIRS_PER_GROUP = GJ * RI;   // per lane
-static_assert(QS >= 2 * PAIRS_PER_GROUP, "queue must absorb one group");
 constexpr int DW = 16;        // queue entries per lane in flight in the drain
 // (the triclinic instantiation is instruction-cache bound: a narrower loop
 // is 9 % faster there, 16 vs 8 is a wash for the others)
 constexpr int DW_TRI = 8;
-static_assert(QS <= 64 && QS % DW == 0, "fail mask is 64 bits; drain is DW-wide");
 
-constexpr int SM_Q = QS * 32 * 4;              // bytes per warp: queue
 constexpr int SM_ST = NSTAGE * 3 * GJ * 4;     // staged j-groups
 constexpr int SM_CODE = NSTAGE * 4;            // their (group, code, quarter mask)
 constexpr int SM_LOG = LOGMAX * 4;             // group log (same words)
@@ -1053,9 +1061,40 @@ constexpr int SM_DUMMY = 32 * 4;               // per-lane sink for dead atomics
 constexpr int SM_QB = 2 * 24 * 4;              // my 4 quarter boxes [6][4], x2:
                                                // prune space and Cartesian
 constexpr int SM_CTX = 32 * 4;                 // per-item constants of the box tests
-constexpr int SM_WARP =
-    SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK + SM_DUMMY + SM_QB + SM_CTX;
-constexpr int SM_FIXED = NWARP * SM_WARP;
+// Per-instantiation part of the layout.  The triclinic kernel keeps the
+// (negated, shifted) i-atoms of the warp in shared memory instead of
+// registers: with them in registers ptxas spilled 9 of the 12 coordinates
+// plus loop state to local memory (276 B; ncu r2a: long_scoreboard 1.8
+// cycles per issue on `LDL`s that miss the 23 KB L1 left beside 2 x 109 KB of
+// shared memory).  Every lane reads back only what it wrote itself, so no
+// synchronisation is involved.  The 1.5 KB per warp are paid for with a
+// shorter queue (56 rows instead of 64).
+template <int BOXKIND>
+struct Lay {
+  static constexpr bool TRI = BOXKIND == RDFK_BOX_TRI;
+  static constexpr int NTHR = TRI ? RDFK_TPB_TRI : TPB;   // threads per CTA
+  static constexpr int NW = NTHR / 32;                    // warps per CTA
+  static constexpr bool IAT_SMEM = TRI && RDFK_IAT_SMEM_TRI;
+  static constexpr int QS = TRI ? RDFK_QS_TRI : QS_MAX;
+  static constexpr int DWK = BOXKIND == RDFK_BOX_TRI ? DW_TRI : DW;
+  static constexpr int SM_Q = QS * 32 * 4;      // bytes per warp: queue
+  static constexpr int SM_IAT = IAT_SMEM ? 3 * CI * 4 : 0;
+  static constexpr int OFF_ST = SM_Q;
+  static constexpr int OFF_CODE = OFF_ST + SM_ST;
+  static constexpr int OFF_LOG = OFF_CODE + SM_CODE;
+  static constexpr int OFF_MARK = OFF_LOG + SM_LOG;
+  static constexpr int OFF_DUMMY = OFF_MARK + SM_MARK;
+  static constexpr int OFF_QB = OFF_DUMMY + SM_DUMMY;
+  static constexpr int OFF_CTX = OFF_QB + SM_QB;
+  static constexpr int OFF_IAT = OFF_CTX + SM_CTX;
+  static constexpr int SM_WARP = OFF_IAT + SM_IAT;
+  static constexpr int SM_FIXED = NW * SM_WARP;
+  static_assert(NTHR % 32 == 0 && NW >= 1 && NW <= 8, "1..8 warps per CTA");
+  static_assert(QS >= PAIRS_PER_GROUP + GJ, "queue must absorb one group");
+  static_assert(QS <= QS_MAX && QS % DWK == 0,
+                "fail mask is 64 bits; drain is DW-wide");
+  static_assert(SM_WARP % 16 == 0, "per-warp areas stay 16-byte aligned");
+};
 
 // hit <=> r2 < cut
 __device__ __forceinline__ void q_push(uint32_t &qaddr, float r2, float cut) {
@@ -1200,7 +1239,8 @@ __device__ __noinline__ int resolve_entry(
 }
 
 template <int BOXKIND, bool GLOBAL_HIST>
-__global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
+__global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
+    const PairArgs a) {
   static_assert(RI == 4 && GJ == 8 && GPC == 16, "written for 4 x 8, 16 groups");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ HistParams s_hp;
@@ -1208,21 +1248,23 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   // warp index through a shuffle: tells the compiler it is warp-uniform, so
   // branches on per-warp shared-memory words need no convergence barriers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  unsigned char *wbase = smem_raw + (size_t)warp * SM_WARP;
+  using L = Lay<BOXKIND>;
+  constexpr int QS = L::QS;
+  constexpr int SM_FIXED = L::SM_FIXED;
+  unsigned char *wbase = smem_raw + (size_t)warp * L::SM_WARP;
   float *q = reinterpret_cast<float *>(wbase);
-  float *jst = reinterpret_cast<float *>(wbase + SM_Q);
-  int *jcode = reinterpret_cast<int *>(wbase + SM_Q + SM_ST);
-  int *glog = reinterpret_cast<int *>(wbase + SM_Q + SM_ST + SM_CODE);
-  unsigned char *mark = wbase + SM_Q + SM_ST + SM_CODE + SM_LOG;
-  const uint32_t dummy_s =
-      smem_u32(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG + SM_MARK) + 4u * lane;
-  float *qb = reinterpret_cast<float *>(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG +
-                                        SM_MARK + SM_DUMMY);   // [6][4]
+  float *jst = reinterpret_cast<float *>(wbase + L::OFF_ST);
+  int *jcode = reinterpret_cast<int *>(wbase + L::OFF_CODE);
+  int *glog = reinterpret_cast<int *>(wbase + L::OFF_LOG);
+  unsigned char *mark = wbase + L::OFF_MARK;
+  const uint32_t dummy_s = smem_u32(wbase + L::OFF_DUMMY) + 4u * lane;
+  float *qb = reinterpret_cast<float *>(wbase + L::OFF_QB);   // [6][4]
+  // my own slots of the warp's i-atom area (triclinic instantiation only)
+  float *iat = reinterpret_cast<float *>(wbase + L::OFF_IAT) + lane;
   // per-item constants that only the box tests read (cluster box, periods, gap
   // scales, lattice vectors) live in shared memory, not in registers: the
   // triclinic instantiation spilled in its hot loops
-  float *ctx = reinterpret_cast<float *>(wbase + SM_Q + SM_ST + SM_CODE + SM_LOG +
-                                         SM_MARK + SM_DUMMY + SM_QB);
+  float *ctx = reinterpret_cast<float *>(wbase + L::OFF_CTX);
   unsigned int *hist_s = reinterpret_cast<unsigned int *>(smem_raw + SM_FIXED);
 
   const int nbins = a.hp.nbins;
@@ -1240,7 +1282,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   unsigned int *wh =
       GLOBAL_HIST ? nullptr : hist_s + (size_t)(warp % copies) * hstride + 1;
   const uint32_t wh_s = GLOBAL_HIST ? 0u : smem_u32(wh);
-  const unsigned int sharers = GLOBAL_HIST ? 1 : (NWARP + copies - 1) / copies;
+  const unsigned int sharers = GLOBAL_HIST ? 1 : (L::NW + copies - 1) / copies;
   const unsigned int flush_limit = (1u << 30) / sharers;
   const uint32_t glog_s = smem_u32(glog), mark_s = smem_u32(mark);
   const uint32_t qw_s = smem_u32(q);   // row r, column c: qw_s + 128 r + 4 c
@@ -1248,9 +1290,9 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
   uint32_t qaddr = qbase;
   const unsigned int lt_mask = (1u << lane) - 1u;
 
-  for (int b = tid; b < copies * hstride; b += TPB) hist_s[b] = 0u;
+  for (int b = tid; b < copies * hstride; b += L::NTHR) hist_s[b] = 0u;
   if (!GLOBAL_HIST)
-    for (int b = tid; b < 2 * nb1; b += TPB) tab_s[b] = a.tables[b];
+    for (int b = tid; b < 2 * nb1; b += L::NTHR) tab_s[b] = a.tables[b];
   if (tid == 0) s_hp = a.hp;
   __syncthreads();
 
@@ -1263,8 +1305,11 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     if (lane == 0) item = atomicAdd(&a.header->work_counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= a.total_items) break;
-    ++n_items;
-    const int f = item / a.ncl_i, ic = item - f * a.ncl_i;
+    // small systems: a (frame, i-cluster) is cut into `nsplit` slices of its
+    // j-clusters so that every warp of the grid gets several items
+    const int slice = item % a.nsplit, fc = item / a.nsplit;
+    if (slice == 0) ++n_items;
+    const int f = fc / a.ncl_i, ic = fc - f * a.ncl_i;
     const FrameParams *fp = a.fparams + f;
     // (or-reductions of identical values: provably warp-uniform flags)
     const int all_slow = __reduce_or_sync(0xffffffffu, fp->all_slow);
@@ -1533,7 +1578,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     // three unrolled copies of the wide loop overflowed the instruction cache
     // of the triclinic instantiation (ncu: no_instruction 3.6 per issue)
     auto drain = [&]() {
-      drain_w(std::integral_constant<int, BOXKIND == RDFK_BOX_TRI ? DW_TRI : DW>());
+      drain_w(std::integral_constant<int, L::DWK>());
     };
     auto drain_small = [&]() { drain_w(std::integral_constant<int, 2>()); };
 
@@ -1598,9 +1643,14 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
         }
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-          nxs[r] = -__fadd_rn(gi_cl[r * 32 + lane], sx);
-          nys[r] = -__fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
-          nzs[r] = -__fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
+          const float vx = -__fadd_rn(gi_cl[r * 32 + lane], sx);
+          const float vy = -__fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
+          const float vz = -__fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
+          if (L::IAT_SMEM) {
+            iat[r * 32] = vx; iat[CI + r * 32] = vy; iat[2 * CI + r * 32] = vz;
+          } else {
+            nxs[r] = vx; nys[r] = vy; nzs[r] = vz;
+          }
         }
         cur_code = code;
       }
@@ -1624,8 +1674,11 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
           if (!((qmask >> r) & 1)) continue;
-          const uint64_t nx2 = pk2(nxs[r], nxs[r]), ny2 = pk2(nys[r], nys[r]),
-                         nz2 = pk2(nzs[r], nzs[r]);
+          const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
+          const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
+          const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
+          const uint64_t nx2 = pk2(nxr, nxr), ny2 = pk2(nyr, nyr),
+                         nz2 = pk2(nzr, nzr);
 #pragma unroll
           for (int up = 0; up < GJ / 2; ++up) {
             const uint64_t dx = add2(xj2[up], nx2), dy = add2(yj2[up], ny2),
@@ -1652,11 +1705,14 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
           if (!((qmask >> r) & 1)) continue;
+          const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
+          const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
+          const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
 #pragma unroll
           for (int u = 0; u < GJ; ++u)
             q_push(qaddr,
-                   pair_r2<BOXKIND, false>(xj8[u], yj8[u], zj8[u], nxs[r], nys[r],
-                                           nzs[r], fb),
+                   pair_r2<BOXKIND, false>(xj8[u], yj8[u], zj8[u], nxr, nyr,
+                                           nzr, fb),
                    cut);
         }
       }
@@ -1672,17 +1728,23 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     // 16 group boxes of two surviving clusters per round.  Surviving groups
     // of the current table class are staged into shared memory by cp.async
     // (each lane copies its own group) and evaluated one after the other.
-    int nrounds, cnt = 0;
+    // t0 .. t1: this slice's part of the j-clusters; `own`: the slice also
+    // takes my own cluster (symmetric schedule, slice 0)
+    int nrounds, t0, t1, own = 0;
     if (a.symmetric) {
       // round 0: my own cluster in full (weight 1: both orders and the self
       // pairs are evaluated); then the circulant half of the others (weight 2)
       const int nt = a.ncl_i;
-      cnt = (nt - 1) / 2;
+      int cnt = (nt - 1) / 2;
       if ((nt & 1) == 0 && ic < nt / 2) ++cnt;
-      nrounds = 1 + (cnt + 31) / 32;
+      t0 = (int)((long long)cnt * slice / a.nsplit);
+      t1 = (int)((long long)cnt * (slice + 1) / a.nsplit);
+      own = slice == 0 ? 1 : 0;
     } else {
-      nrounds = (a.ncl_j + 31) / 32;
+      t0 = (int)((long long)a.ncl_j * slice / a.nsplit);
+      t1 = (int)((long long)a.ncl_j * (slice + 1) / a.nsplit);
     }
+    nrounds = own + (t1 - t0 + 31) / 32;
     // which table classes occur in this frame
     int cls_lo = 0, cls_hi = 1;
     if (all_slow) cls_lo = cls_hi = 1;             // class is ignored
@@ -1690,28 +1752,28 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
     else if (!shift_ok) cls_lo = 1;
     for (cls = cls_lo; cls <= cls_hi; ++cls) {
       cut = cls ? cut1 : cut0;
-      weight = 1u;
+      weight = (a.symmetric && !own) ? 2u : 1u;
       for (int rr = 0; rr < nrounds; ++rr) {
         int c = 0;
         bool cv;
         if (a.symmetric) {
-          if (rr == 0) {
+          if (rr < own) {
             c = ic;
             cv = lane == 0;
           } else {
-            if (rr == 1) {   // leaving my own cluster: the weight changes
+            if (own && rr == 1) {   // leaving my own cluster: the weight changes
               if (!all_slow) drain_small();
               weight = 2u;
             }
-            const int t = (rr - 1) * 32 + lane;
-            cv = t < cnt;
+            const int t = t0 + (rr - own) * 32 + lane;
+            cv = t < t1;
             c = ic + 1 + t;
             if (c >= a.ncl_j) c -= a.ncl_j;
             if (!cv) c = 0;
           }
         } else {
-          c = rr * 32 + lane;
-          cv = c < a.ncl_j;
+          c = t0 + rr * 32 + lane;
+          cv = c < t1;
           if (!cv) c = 0;
         }
         int dummy;
@@ -1768,7 +1830,7 @@ __global__ __launch_bounds__(TPB, 2) void pair_prune_kernel(const PairArgs a) {
 
   __syncthreads();
   if (!GLOBAL_HIST) {
-    for (int b = tid; b < nbins; b += TPB) {
+    for (int b = tid; b < nbins; b += L::NTHR) {
       unsigned long long s = 0;
       for (int c = 0; c < copies; ++c) s += hist_s[(size_t)c * hstride + 1 + b];
       if (s) atomicAdd(a.hist + b, s);
@@ -1915,6 +1977,31 @@ __global__ __launch_bounds__(256) void sites_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// InterRDF_s epilogue on the device (pmda/rdf.py:311-334): the per-block
+// uint32 counts become the float64 tensors the reference returns
+// (`count[i][a, b, :]`, pmda/rdf.py:294-295), their sum over the blocks
+// (`np.sum(self._results[:, 0])`, exact: integers below 2^53) and
+//   rdf = count / den[bin],   den = density * vol * n_frames   (host, [nbins])
+// -- one IEEE double division per cell, the same operation numpy performs, so
+// the bits are numpy's.  One thread per (cell, bin).
+// ---------------------------------------------------------------------------
+__global__ __launch_bounds__(256) void sites_finish_kernel(
+    const unsigned int *__restrict__ count, int n_blocks, long long n, int nbins,
+    const double *__restrict__ den, double *__restrict__ count_f64,
+    double *__restrict__ total, double *__restrict__ rdf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double sum = 0.0;
+  for (int b = 0; b < n_blocks; ++b) {
+    const double c = (double)count[(size_t)b * n + i];
+    if (count_f64) count_f64[(size_t)b * n + i] = c;
+    sum = __dadd_rn(sum, c);
+  }
+  if (total) total[i] = sum;
+  if (rdf) rdf[i] = __ddiv_rn(sum, den[i % nbins]);
+}
+
+// ---------------------------------------------------------------------------
 // Trajectory ingest: frames as they lie in a DCD file (per frame three
 // Fortran records x[N], y[N], z[N] of float32, optionally preceded by a unit
 // cell record) -> the [F][N][3] layout of ts.positions that every kernel above
@@ -2009,15 +2096,25 @@ __global__ __launch_bounds__(256) void ffma_peak_kernel(float *out, int iters,
 // ---------------------------------------------------------------------------
 // host side of the C ABI
 // ---------------------------------------------------------------------------
+// (device attributes never change: looked up once per device; plain ints
+// written after the values are complete -- a racing thread at worst repeats
+// the same queries)
 static int check_device(int *sm_count) {
+  static int cached_sms[64];
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64) {
+    const int c = __atomic_load_n(&cached_sms[dev], __ATOMIC_ACQUIRE);
+    if (c > 0) { *sm_count = c; return RDFK_OK; }
+  }
   int major = 0, sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (major != 10)
     return set_err(RDFK_EARCH, "librdfk is built for sm_100a only%s%s");
   *sm_count = sms;
+  if (dev >= 0 && dev < 64)
+    __atomic_store_n(&cached_sms[dev], sms, __ATOMIC_RELEASE);
   return RDFK_OK;
 }
 
@@ -2162,6 +2259,7 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   if (total > 0x7fff0000LL)
     return set_err(RDFK_EINVAL, "too many cluster work items in one call; "
                                 "pass fewer frames%s%s");
+  a.nsplit = 1;
   a.total_items = (int)total;
   a.fparams = fparams; a.tables = tables; a.hp = hp; a.hist = hist;
   a.header = header;
@@ -2169,28 +2267,68 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   // an SM, otherwise as many as one CTA can hold, otherwise global atomics
   const size_t per_copy = ((size_t)hp.nbins + 1) * sizeof(unsigned int);
   const size_t tab_bytes = 2 * ((size_t)hp.nbins + 1) * sizeof(float2) + 16;
-  const size_t two_cta = (size_t)(227 * 1024) / 2 - 1024 - SM_FIXED;
-  const size_t one_cta = (size_t)(227 * 1024) - 1024 - SM_FIXED;
+  constexpr int SM_FIXED = Lay<BOXKIND>::SM_FIXED;
+  // (two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA, 128 B
+  // of static shared memory in the kernel)
+  const size_t two_cta = (size_t)(228 * 1024) / 2 - 1024 - 128 - SM_FIXED;
+  const size_t one_cta = (size_t)(227 * 1024) - 1024 - 128 - SM_FIXED;
   int copies = 0;
-  if ((size_t)NWARP * per_copy + tab_bytes <= two_cta) copies = NWARP;
+  constexpr int NW = Lay<BOXKIND>::NW, NTHR = Lay<BOXKIND>::NTHR;
+  if ((size_t)NW * per_copy + tab_bytes <= two_cta) copies = NW;
   else if (per_copy + tab_bytes <= one_cta)
     copies = (int)((one_cta - tab_bytes) / per_copy);
-  if (copies > NWARP) copies = NWARP;
+  if (copies > NW) copies = NW;
   a.hist_copies = copies;
   const size_t smem =
       (size_t)SM_FIXED + (copies ? (size_t)copies * per_copy + tab_bytes : 0);
   void (*kern)(const PairArgs) = copies ? pair_prune_kernel<BOXKIND, false>
                                         : pair_prune_kernel<BOXKIND, true>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem));
-  if (occ < 1) return set_err(RDFK_ECUDA, "pair_prune_kernel does not fit%s%s");
+  // the attribute / occupancy queries cost more than a launch: remembered per
+  // (device, instantiation, shared-memory size); thread_local, no locking
+  struct OccCache { int dev; void *fn; size_t smem; int occ; };
+  static thread_local OccCache occ_cache[8];
+  static thread_local int occ_next = 0;
+  int dev = 0, occ = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  for (int i = 0; i < 8; ++i)
+    if (occ_cache[i].occ > 0 && occ_cache[i].dev == dev &&
+        occ_cache[i].fn == (void *)kern && occ_cache[i].smem == smem)
+      occ = occ_cache[i].occ;
+  if (occ == 0) {
+    // (the opt-in maximum, so that a later, smaller request of another call
+    // can never lower the limit under a remembered larger one)
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin,
+                                    cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if ((size_t)optin < smem + 128)
+      return set_err(RDFK_ECUDA, "pair_prune_kernel does not fit%s%s");
+    CUDA_TRY(cudaFuncSetAttribute(
+        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 128));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHR, smem));
+    if (occ < 1) return set_err(RDFK_ECUDA, "pair_prune_kernel does not fit%s%s");
+    occ_cache[occ_next] = OccCache{dev, (void *)kern, smem, occ};
+    occ_next = (occ_next + 1) & 7;
+  }
   long long grid = (long long)sms * occ;
-  const long long need = (total + NWARP - 1) / NWARP;
+  {
+    // Small systems: with fewer than ~8 work items per resident warp the
+    // kernel's time is that of the unluckiest warp (config 1: 2400 items for
+    // 2368 warps, so 32 warps do two items while the rest idle).  Cut every
+    // item into slices of its j-clusters.
+    const long long warps = grid * NW;
+    const long long jparts = same_group ? (a.ncl_j - 1) / 2 : a.ncl_j;
+    long long ns = (8 * warps + total - 1) / total;
+    if (ns > 8) ns = 8;
+    if (ns > jparts) ns = jparts;
+    if (ns < 1) ns = 1;
+    if (total * ns > 0x7fff0000LL) ns = 1;
+    a.nsplit = (int)ns;
+    a.total_items = (int)(total * ns);
+  }
+  const long long need = ((long long)a.total_items + NW - 1) / NW;
   if (grid > need) grid = need;
   if (grid > 0) {
-    kern<<<(int)grid, TPB, smem, st>>>(a);
+    kern<<<(int)grid, NTHR, smem, st>>>(a);
     COUNT_LAUNCH(1);
   }
 
@@ -2299,6 +2437,28 @@ extern "C" int rdfk_rdf_sites(const float *xyz, int F, int natoms,
           xyz, natoms, idxA, idxB, offA, offB, cell_off, n_sites, total_cells,
           box, hp, count);
   }
+  COUNT_LAUNCH(1);
+  CUDA_TRY(cudaGetLastError());
+  return RDFK_OK;
+}
+
+extern "C" int rdfk_sites_finish(const unsigned int *count, int n_blocks,
+                                 long long n, int nbins, const double *den,
+                                 double *count_f64, double *total, double *rdf,
+                                 void *stream) {
+  if (n_blocks < 0 || n < 0 || nbins < 1)
+    return set_err(RDFK_EINVAL, "negative size or nbins < 1%s%s");
+  if (n == 0 || n_blocks == 0) return RDFK_OK;
+  if (!count || (rdf && !den) || (!count_f64 && !total && !rdf))
+    return set_err(RDFK_EINVAL, "null pointer argument%s%s");
+  if (n % nbins) return set_err(RDFK_EINVAL, "n is not a multiple of nbins%s%s");
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  const long long blocks = (n + 255) / 256;
+  if (blocks > 0x7fffffffLL) return set_err(RDFK_EINVAL, "too many cells%s%s");
+  sites_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      count, n_blocks, n, nbins, den, count_f64, total, rdf);
   COUNT_LAUNCH(1);
   CUDA_TRY(cudaGetLastError());
   return RDFK_OK;

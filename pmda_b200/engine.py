@@ -45,6 +45,15 @@ class Config(object):
     compute_streams = int(os.environ.get("PMDA_B200_COMPUTE_STREAMS", 2))
     #: uncached runs: first batch = 1/head_divisor of the frames (0: off)
     head_divisor = int(os.environ.get("PMDA_B200_HEAD_DIVISOR", 16))
+    #: ... but only when the run uploads at least this many bytes: for a small
+    #: run a second launch costs more than the upload it would hide
+    head_min_bytes = int(os.environ.get("PMDA_B200_HEAD_MIN_BYTES", 64 << 20))
+    #: host threads gathering the atoms an analysis references into the
+    #: pinned ring (InterRDF_s: only those atoms cross PCIe)
+    gather_threads = int(os.environ.get(
+        "PMDA_B200_GATHER_THREADS",
+        max(1, min(16, (os.cpu_count() or 1) //
+                   max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))))
     #: page-lock in-memory trajectories so H2D runs straight from them
     pin_host = os.environ.get("PMDA_B200_PIN_HOST", "1") != "0"
     #: host threads copying frame blocks into the pinned ring
@@ -86,6 +95,8 @@ class CudaBackend(object):
     hbonds_workspace_bytes = staticmethod(_cabi.hbonds_workspace_bytes)
     hbonds = staticmethod(_cabi.hbonds)
     host_hash_rows = staticmethod(_cabi.host_hash_rows)
+    host_gather_rows = staticmethod(_cabi.host_gather_rows)
+    sites_finish = staticmethod(_cabi.sites_finish)
 
 
 _backend = CudaBackend()
@@ -128,6 +139,10 @@ class _DeviceState(object):
         self.cache_used = 0
         #: wrapped-frames counter of each workspace at the last report
         self.wrapped_seen = {}
+        #: small device constants (edges, index lists, box rows) by content
+        self.consts = OrderedDict()
+        #: page-locked landing buffer of a run's results
+        self.result_pin = None
         if self.is_cuda:
             with torch.cuda.device(device):
                 self.copy_stream = torch.cuda.Stream(device)
@@ -143,6 +158,31 @@ class _DeviceState(object):
     @property
     def compute_stream(self):
         return self.compute_streams[self.cur]
+
+    # staging buffers are flat and only ever grow: analyses of different
+    # shapes taking turns on a device must not re-allocate (page-locking
+    # memory costs milliseconds)
+    def pinned_view(self, slot, n_frames, n_atoms):
+        need = max(1, n_frames * n_atoms * 3)
+        buf = self.pinned[slot]
+        if buf is None or buf.numel() < need:
+            self.pinned[slot] = None
+            buf = self.pinned[slot] = torch.empty(
+                max(need, 1 << 16), dtype=torch.float32, pin_memory=True)
+        return buf[:n_frames * n_atoms * 3].view(n_frames, n_atoms, 3)
+
+    def staged_view(self, slot, n_frames, n_atoms):
+        need = max(1, n_frames * n_atoms * 3)
+        buf = self.staged[slot]
+        if buf is None or buf.numel() < need:
+            if buf is not None and self.is_cuda:
+                # still read by copies / kernels queued on other streams
+                for cs in self.compute_streams + [self.copy_stream]:
+                    buf.record_stream(cs)
+            self.staged[slot] = None
+            buf = self.staged[slot] = torch.empty(
+                max(need, 1 << 16), dtype=torch.float32, device=self.device)
+        return buf[:n_frames * n_atoms * 3].view(n_frames, n_atoms, 3)
 
     def sync_compute(self):
         for cs in self.compute_streams:
@@ -394,6 +434,48 @@ def _read_frames(traj, frames):
     return pos, np.stack(dims)
 
 
+def _dev_const(st, arr, dtype):
+    """Device copy of a small host array, looked up by CONTENT: run() is
+    called again and again with the same edges / AtomGroup indices / box rows
+    (often on a fresh analysis object), and every pageable upload is a
+    synchronous ~15 us round trip."""
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    if a.nbytes > (64 << 20):
+        return torch.as_tensor(a, device=st.device)
+    key = (a.dtype.str, a.shape,
+           _backend.host_hash_rows(a.reshape(1, -1).view(np.uint8), 1, 1))
+    hit = st.consts.get(key)
+    if hit is not None:
+        st.consts.move_to_end(key)
+        return hit
+    t = torch.as_tensor(a, device=st.device)
+    if st.is_cuda:
+        # uploaded on torch's current stream; every later user runs on a
+        # compute stream
+        torch.cuda.current_stream(st.device).synchronize()
+    st.consts[key] = t
+    while len(st.consts) > 256:
+        st.consts.popitem(last=False)
+    return t
+
+
+_box_cache = OrderedDict()
+
+
+def _box_row(row):
+    """(kind, box9, volume) of one `dimensions` row, remembered by content"""
+    key = row.tobytes()
+    hit = _box_cache.get(key)
+    if hit is None:
+        kind, b = mdamath.classify_box(row)
+        vol = float(mdamath.box_volume(row)) if kind != _cabi.BOX_NONE else 0.0
+        hit = (kind, np.asarray(b, dtype=np.float32), vol)
+        _box_cache[key] = hit
+        while len(_box_cache) > 1024:
+            _box_cache.popitem(last=False)
+    return hit
+
+
 def _box_rows(dims, n):
     """per-frame (kind, box9, volume) with one host evaluation per distinct box"""
     kinds = np.zeros(n, dtype=np.int32)
@@ -408,8 +490,7 @@ def _box_rows(dims, n):
         uniq, inv = np.unique(d, axis=0, return_inverse=True)
         inv = inv.reshape(-1)
     for u, row in enumerate(uniq):
-        kind, b = mdamath.classify_box(row)
-        vol = float(mdamath.box_volume(row)) if kind != _cabi.BOX_NONE else 0.0
+        kind, b, vol = _box_row(np.ascontiguousarray(row, dtype=np.float32))
         sel = inv == u
         kinds[sel] = kind
         box9[sel] = b
@@ -457,9 +538,16 @@ def _frame_shards(blocks, n_parts):
 class _Pipeline(object):
     """Feeds frame batches of one trajectory to one device, double buffered."""
 
-    def __init__(self, st, traj, natoms):
-        self.st, self.traj, self.natoms = st, traj, natoms
-        self.frame_bytes = natoms * 12
+    def __init__(self, st, traj, natoms, gather=None):
+        """`gather`: sorted int32 atom indices -- only these atoms go to the
+        device (as xyz [B, len(gather), 3], in this order)"""
+        self.st, self.traj = st, traj
+        self.natoms_traj = natoms
+        self.gather = gather
+        if gather is not None:
+            natoms = len(gather)
+        self.natoms = natoms
+        self.frame_bytes = max(1, natoms) * 12
         nb = max(1, Config.batch_bytes // max(1, self.frame_bytes))
         self.batch_frames = int(min(nb, Config.max_batch_frames))
         self.dslot = 0
@@ -472,9 +560,15 @@ class _Pipeline(object):
         #: current data on every hit.  Other readers are never cached.
         self.cheap_reads = getattr(traj, "frame_block", None) is not None
         #: file formats whose frames can go to the device as they lie on disk
-        self.raw = getattr(traj, "raw_block", None) if st.is_cuda else None
+        self.raw = getattr(traj, "raw_block", None) \
+            if (st.is_cuda and gather is None) else None
+        # Gathered blocks are never cached: validating a cached copy means
+        # reading every referenced atom of the host data again, which is the
+        # gather itself -- re-gathering costs the same host pass and the
+        # (3x smaller) upload hides behind it.
         self.traj_key = _traj_token(traj) \
-            if (self.cheap_reads or self.raw is not None) else None
+            if (gather is None and
+                (self.cheap_reads or self.raw is not None)) else None
         #: cache hits of this run whose host data is still being hashed:
         #: (key, entry, Future of the current data's hash)
         self.pending = []
@@ -493,7 +587,8 @@ class _Pipeline(object):
         streaming = self.st.is_cuda and (self.traj_key is None
                                          or Config.cache_bytes <= 0)
         if streaming and Config.head_divisor > 0 \
-                and n >= 4 * Config.head_divisor:
+                and n >= 4 * Config.head_divisor \
+                and n * self.frame_bytes >= Config.head_min_bytes:
             # frames come from the host every time: a short first batch, whose
             # upload is the only one no kernel hides (its own kernel tail is
             # covered by the next batch on the other compute stream)
@@ -501,6 +596,10 @@ class _Pipeline(object):
             yield frames[:head]
         rest = n - head
         nb = -(-rest // self.batch_frames)
+        if self.gather is not None and streaming and rest >= 64:
+            # the host gather of batch k+1 runs beside the upload and the
+            # kernels of batch k: a few batches even when one would hold all
+            nb = max(nb, 4)
         size = -(-rest // nb)
         for lo in range(head, n, size):
             yield frames[lo:lo + size]
@@ -512,6 +611,8 @@ class _Pipeline(object):
         use_cache = self.traj_key is not None and Config.cache_bytes > 0
         pos = dims = None
         key = None
+        if self.gather is not None:
+            return self._fetch_gather(frames, t0)
         rb = self.raw(frames) if self.raw is not None else None
         if rb is not None:
             return self._fetch_raw(frames, rb, use_cache, t0)
@@ -550,8 +651,6 @@ class _Pipeline(object):
                 st.cache[key] = _CacheEntry(xyz_dev, nbytes, hfut)
                 st.cache_used += nbytes
             return xyz_dev, dims, time.time() - t0, None
-        cap = self.batch_frames
-        shape = (cap, self.natoms, 3)
         slot = None
         with torch.cuda.device(st.device):
             # destination: a cache entry of its own, or a rotating buffer
@@ -561,13 +660,9 @@ class _Pipeline(object):
             else:
                 slot = self.dslot
                 self.dslot ^= 1
-                if st.staged[slot] is None or st.staged[slot].shape != shape:
-                    st.staged[slot] = None
-                    st.staged[slot] = torch.empty(shape, dtype=torch.float32,
-                                                  device=st.device)
                 if self.compute_done[slot] is not None:
                     st.copy_stream.wait_event(self.compute_done[slot])
-                xyz_dev = st.staged[slot][:B]
+                xyz_dev = st.staged_view(slot, B, self.natoms)
             # source: the trajectory array itself when it is page-locked,
             # otherwise a rotating pinned staging buffer
             src = None
@@ -579,13 +674,10 @@ class _Pipeline(object):
             if src is None:
                 ps = self.pslot
                 self.pslot ^= 1
-                if st.pinned[ps] is None or st.pinned[ps].shape != shape:
-                    st.pinned[ps] = torch.empty(shape, dtype=torch.float32,
-                                                pin_memory=True)
                 if self.h2d_done[ps] is not None:
                     self.h2d_done[ps].synchronize()
-                _copy_frames(st.pinned[ps][:B].numpy(), pos)
-                src = st.pinned[ps][:B]
+                src = st.pinned_view(ps, B, self.natoms)
+                _copy_frames(src.numpy(), pos)
             else:
                 ps = None
             with torch.cuda.stream(st.copy_stream):
@@ -598,6 +690,44 @@ class _Pipeline(object):
         if cacheable:
             st.cache[key] = _CacheEntry(xyz_dev, nbytes, hfut)
             st.cache_used += nbytes
+        return xyz_dev, dims, time.time() - t0, slot
+
+    def _fetch_gather(self, frames, t0):
+        """only the atoms of `self.gather`: host gather (threaded, native)
+        straight into the pinned ring, upload from there"""
+        st = self.st
+        pos, dims = _read_frames(self.traj, frames)
+        B = len(frames)
+        if pos.shape[1:] != (self.natoms_traj, 3):
+            raise ValueError("trajectory frame has %r atoms, expected %d"
+                             % (pos.shape[1:], self.natoms_traj))
+        if pos.dtype != np.float32 or (B and not pos[0].flags.c_contiguous):
+            pos = np.ascontiguousarray(pos, dtype=np.float32)
+        ng = self.natoms
+        if not st.is_cuda:
+            host = np.empty((B, ng, 3), dtype=np.float32)
+            _backend.host_gather_rows(pos, self.gather, host,
+                                      Config.gather_threads)
+            return torch.from_numpy(host), dims, time.time() - t0, None
+        with torch.cuda.device(st.device):
+            ps = self.pslot
+            self.pslot ^= 1
+            if self.h2d_done[ps] is not None:
+                self.h2d_done[ps].synchronize()         # pinned slot is free
+            pin = st.pinned_view(ps, B, ng)
+            _backend.host_gather_rows(pos, self.gather, pin.numpy(),
+                                      Config.gather_threads)
+            slot = self.dslot
+            self.dslot ^= 1
+            if self.compute_done[slot] is not None:
+                st.copy_stream.wait_event(self.compute_done[slot])
+            xyz_dev = st.staged_view(slot, B, ng)
+            with torch.cuda.stream(st.copy_stream):
+                xyz_dev.copy_(pin, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st.copy_stream)
+            self.h2d_done[ps] = ev
+            st.compute_stream.wait_event(ev)
         return xyz_dev, dims, time.time() - t0, slot
 
     def verify(self):
@@ -666,12 +796,7 @@ class _Pipeline(object):
             else:
                 slot = self.dslot
                 self.dslot ^= 1
-                shape = (self.batch_frames, self.natoms, 3)
-                if st.staged[slot] is None or st.staged[slot].shape != shape:
-                    st.staged[slot] = None
-                    st.staged[slot] = torch.empty(shape, dtype=torch.float32,
-                                                  device=st.device)
-                xyz_dev = st.staged[slot][:B]
+                xyz_dev = st.staged_view(slot, B, self.natoms)
             # the transpose runs on the compute stream, in order with the
             # kernels that read (and last read) xyz_dev
             _backend.unpack_planes(st.raw_dev[rs], fstride, offs[0], offs[1],
@@ -739,13 +864,36 @@ def _as_u64_ptr_tensor(t):
     return t  # int64 storage, the kernels treat it as uint64
 
 
+def _result_to_host(st, res, stream):
+    """one D2H copy of a run's device results into the device's page-locked
+    landing buffer, behind everything queued on `stream` -> int64 numpy view
+    (valid until the next run on this device)"""
+    n = res.numel()
+    if not st.is_cuda:
+        return res.numpy()
+    pin = st.result_pin
+    if pin is None or pin.numel() < n:
+        st.result_pin = None
+        pin = st.result_pin = torch.empty(max(n, 4096), dtype=torch.int64,
+                                          pin_memory=True)
+    with torch.cuda.stream(stream):
+        pin[:n].copy_(res, non_blocking=True)
+    stream.synchronize()
+    return pin[:n].numpy()
+
+
 def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
-                  same_group, nbins, rng, edges, excl):
-    """All frames of one local device.  -> dict of partial results"""
+                  same_group, nbins, rng, edges, excl, n_extra=0):
+    """All frames of one local device: stage the batches and queue the
+    kernels.  Nothing here waits for the GPU.  -> dict of partial results;
+    ``res`` is a device int64 vector ``[16 | n_blocks * nbins | n_extra]``:
+    the counters of the two workspaces (rdfk.h, rdfk_rdf_stats), the block
+    histograms, and room for what the caller wants to send along in the one
+    all-reduce of the run."""
     st = _state(device)
     be = _backend
     out = {
-        "hist": None,
+        "res": None, "timers": [], "pipe": None, "st": st,
         "vol": np.zeros(n_frames, dtype=np.float64),
         "io": np.zeros(n_frames, dtype=np.float64),
         "compute": np.zeros(n_frames, dtype=np.float64),
@@ -755,23 +903,23 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
         cuda = st.is_cuda
         ctx = torch.cuda.device(device) if cuda else _nullctx()
         with ctx:
-            hist = torch.zeros((n_blocks, nbins), dtype=torch.int64,
-                               device=device)
-            edges_d = torch.as_tensor(edges, dtype=torch.float64,
-                                      device=device)
-            i1 = _to_dev_i32(idx1, device)
-            i2 = i1 if same_group else _to_dev_i32(idx2, device)
+            n_streams = max(1, min(2, Config.compute_streams)) if cuda else 1
+            st.cur = 0
+            cs = st.compute_streams
+            with (torch.cuda.stream(cs[0]) if cuda else _nullctx()):
+                res = torch.zeros(16 + n_blocks * nbins + n_extra,
+                                  dtype=torch.int64, device=device)
+            hist = res[16:16 + n_blocks * nbins].view(n_blocks, nbins)
+            edges_d = _dev_const(st, edges, np.float64)
+            i1 = _dev_const(st, idx1, np.int32)
+            i2 = i1 if same_group else _dev_const(st, idx2, np.int32)
             n1, n2 = len(idx1), len(idx2)
             pipe = _Pipeline(st, traj, natoms)
             ws_bytes = be.rdf_workspace_bytes(pipe.batch_frames, n1, n2, nbins,
                                               same_group)
-            timers = []
-            n_streams = max(1, min(2, Config.compute_streams)) if cuda else 1
-            st.cur = 0
-            if cuda:
-                # the zero-fill / uploads above ran on the current stream
-                for cs in st.compute_streams:
-                    cs.wait_stream(torch.cuda.current_stream(device))
+            timers = out["timers"]
+            if cuda and n_streams > 1:
+                cs[1].wait_stream(cs[0])          # the zero-fill of `res`
             n_batch = 0
             for (b, pos0, frames) in segs:
                 done = 0
@@ -785,16 +933,7 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     lo_f = pos0 + done
                     out["vol"][lo_f:lo_f + B] = vols
                     out["io"][lo_f:lo_f + B] = t_io / B
-                    # allocated and filled on the batch's compute stream: the
-                    # host runs batches ahead of the device, and a block freed
-                    # on another stream could be handed out again (and
-                    # overwritten) while this batch's kernels still wait
-                    with (torch.cuda.stream(st.compute_stream) if cuda
-                          else _nullctx()):
-                        box_d = torch.as_tensor(box9, device=device)
-                    if cuda:
-                        st.compute_stream.wait_stream(
-                            torch.cuda.current_stream(device))
+                    box_d = _dev_const(st, box9, np.float32)
                     out["first_launch"][b] = min(out["first_launch"][b],
                                                  time.time())
                     tm = _Timer(st)
@@ -809,40 +948,41 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     pipe.mark_compute_done(slot)
                     timers.append((tm, lo_f, B))
                     done += B
-            # the counters librdfk keeps in the first 64 bytes of a workspace
-            # (rdfk.h, rdfk_rdf_stats), fetched behind the last kernels
-            stats_host = []
             if cuda:
-                for k in range(n_streams):
+                # the counters librdfk keeps in the first 64 bytes of each
+                # workspace travel with the histograms
+                for k in range(min(n_streams, n_batch)):
                     ws_k = st.workspaces[k]
-                    if ws_k is None or n_batch <= k:
-                        continue
                     off = (-ws_k.data_ptr()) % 256
-                    with torch.cuda.stream(st.compute_streams[k]):
-                        stats_host.append(
-                            ws_k[off:off + 64].view(torch.int64).to(
-                                "cpu", non_blocking=True))
-            prev = None
-            for tm, lo_f, B in timers:
-                # batches on alternating streams overlap: a batch is charged
-                # from the end of the previous one (or its own start, if later)
-                out["compute"][lo_f:lo_f + B] = tm.seconds(after=prev) / B
-                prev = tm
-            if cuda:
-                st.sync_compute()
-            pipe.verify()       # cache hits still match the trajectory?
+                    with torch.cuda.stream(cs[k]):
+                        res[8 * k:8 * k + 8].copy_(
+                            ws_k[off:off + 64].view(torch.int64),
+                            non_blocking=True)
+                if n_streams > 1 and n_batch > 1:
+                    cs[0].wait_stream(cs[1])      # cs[0] now ends the run
             st.cur = 0
-            out["hist"] = hist
-            _check_stats(st, stats_host)
+            out["res"], out["pipe"] = res, pipe
     return out
+
+
+def _part_timers(out):
+    """CUDA-event seconds of a part's batches -> out["compute"] (waits for
+    the batches)"""
+    prev = None
+    for tm, lo_f, B in out["timers"]:
+        # batches on alternating streams overlap: a batch is charged from
+        # the end of the previous one (or its own start, if later)
+        out["compute"][lo_f:lo_f + B] = tm.seconds(after=prev) / B
+        prev = tm
+    out["timers"] = []
 
 
 def _check_stats(st, stats_host):
     """act on librdfk's workspace counters after a run (rdfk.h): internal
     violations are fatal; atoms outside the primary triclinic cell are
-    reported once per growth of the counter"""
-    for k, t in enumerate(stats_host):
-        s = t.numpy()
+    reported once per growth of the counter.  `stats_host`: one int64[8]
+    per workspace."""
+    for k, s in enumerate(stats_host):
         if s[6]:
             raise _cabi.RdfkError(
                 "librdfk internal check failed %d time(s), first code %d: the "
@@ -969,6 +1109,83 @@ def _finish(hist_np, vol, io, compute, first_launch, blocks, make_result):
     return res
 
 
+def _local_parts(fn, devices, parts, fetch_now):
+    """Queue the parts on the local devices, wait for them and make sure
+    every cached frame block they used still matches the trajectory (stale
+    blocks are evicted and everything runs again: the kernels had already
+    consumed them).  With `fetch_now` (one device, one rank: nothing to
+    exchange) the device results come to the host behind the last kernel, so
+    the run has a single synchronisation.  -> (outs, host result or None)"""
+    for _ in range(4):
+        outs = _run_parts(fn, devices, parts)
+        host = None
+        if fetch_now:
+            st = outs[0]["st"]
+            with st.lock:
+                host = _result_to_host(st, outs[0]["res"],
+                                       st.compute_streams[0])
+        else:
+            for o in outs:
+                if o["st"].is_cuda:
+                    o["st"].compute_streams[0].synchronize()
+        try:
+            for o in outs:
+                with o["st"].lock:
+                    o["pipe"].verify()
+        except _StaleFrames:
+            continue
+        for o in outs:
+            _part_timers(o)
+        return outs, host
+    raise RuntimeError("the trajectory kept changing while run() was "
+                       "reading it")
+
+
+def _exchange(outs, host, n_main, n_frames):
+    """The epilogue of a run: per-frame volumes / staging / kernel seconds of
+    all local parts join the device results and cross the ranks in ONE
+    all-reduce (float64 bit patterns ride along as int64: every frame is
+    owned by exactly one rank, the others contribute zeros, and x + 0 is
+    exact on the bits); one D2H copy.  -> (main int64 [n_main] of the whole
+    job, extras float64 [3, n_frames], per-workspace counters of this rank)"""
+    world = _dist_world()
+    ext = np.stack([sum(o["vol"] for o in outs), sum(o["io"] for o in outs),
+                    sum(o["compute"] for o in outs)])
+    if host is not None:                  # one device, one rank: all here
+        return host[16:16 + n_main], ext, [host[0:8], host[8:16]]
+    stats = []
+    if len(outs) == 1:
+        o = outs[0]
+        st, res = o["st"], o["res"]
+        cs0 = st.compute_streams[0]
+        with st.lock:
+            with (torch.cuda.stream(cs0) if st.is_cuda else _nullctx()):
+                if world > 1:
+                    bits = torch.from_numpy(
+                        np.ascontiguousarray(ext).reshape(-1).view(np.int64))
+                    res[16 + n_main:].copy_(bits)
+                    _allreduce(res[16:])
+            full = _result_to_host(st, res, cs0)
+        stats = [full[0:8], full[8:16]]
+        main = full[16:16 + n_main]
+        if world > 1:
+            ext = full[16 + n_main:].view(np.float64).reshape(3, n_frames)
+        return main, ext, stats
+    # several local devices (n_jobs > 1): summed on the host
+    total = np.zeros(n_main + 3 * n_frames, dtype=np.int64)
+    for o in outs:
+        with o["st"].lock:
+            full = _result_to_host(o["st"], o["res"],
+                                   o["st"].compute_streams[0]).copy()
+        _check_stats(o["st"], [full[0:8], full[8:16]])
+        total[:n_main] += full[16:16 + n_main]
+    total[n_main:] = np.ascontiguousarray(ext).reshape(-1).view(np.int64)
+    if world > 1:
+        total = _allreduce(torch.from_numpy(total)).numpy()
+    return (total[:n_main],
+            total[n_main:].view(np.float64).reshape(3, n_frames), [])
+
+
 def run_rdf_blocks(traj, natoms, idx1, idx2, same_group, blocks, nbins, rng,
                    edges, excl, n_jobs):
     """InterRDF over frame blocks.  -> list of per-block tuples whose first
@@ -978,21 +1195,21 @@ def run_rdf_blocks(traj, natoms, idx1, idx2, same_group, blocks, nbins, rng,
     devices = _backend.devices(n_jobs)
     n_blocks = len(blocks)
     parts, n_frames = _shard_for_this_rank(blocks, devices)
+    world = _dist_world()
+    n_extra = 3 * n_frames if world > 1 else 0
 
     def fn(device, segs):
         return _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames,
-                             idx1, idx2, same_group, nbins, rng, edges, excl)
+                             idx1, idx2, same_group, nbins, rng, edges, excl,
+                             n_extra)
 
-    outs = _run_parts(fn, devices, parts)
-    hist = _combine(outs, devices[0], n_blocks, nbins, torch.int64)
-    hist = _allreduce(hist)                      # the one NCCL all-reduce
-    extra = np.stack([sum(o["vol"] for o in outs),
-                      sum(o["io"] for o in outs),
-                      sum(o["compute"] for o in outs)])
-    if _dist_world() > 1:
-        extra = _allreduce(torch.from_numpy(extra)).numpy()
+    outs, host = _local_parts(fn, devices, parts,
+                              fetch_now=(world == 1 and len(devices) == 1))
+    main, extra, stats = _exchange(outs, host, n_blocks * nbins, n_frames)
+    if stats:
+        _check_stats(outs[0]["st"], stats)
     first = np.min(np.stack([o["first_launch"] for o in outs]), axis=0)
-    hist_np = hist.cpu().numpy()
+    hist_np = main.reshape(n_blocks, nbins)
 
     def make_result(b, count, vol):
         r = np.empty(2, dtype=object)

@@ -220,8 +220,10 @@ def test_head_batch_never_exceeds_the_batch_size():
             raise AssertionError
 
     old = engine.Config.cache_bytes, engine.Config.batch_bytes
+    old_min = engine.Config.head_min_bytes
     try:
         engine.Config.cache_bytes = 0
+        engine.Config.head_min_bytes = 0
         engine.Config.batch_bytes = 111 * 1000 * 12
         pipe = engine._Pipeline(St(), Traj(), 1000)
         assert pipe.batch_frames == 111
@@ -230,7 +232,12 @@ def test_head_batch_never_exceeds_the_batch_size():
         assert sizes[0] == 111
         sizes = [len(b) for b in pipe.batches(range(800))]
         assert sum(sizes) == 800 and max(sizes) <= 111 and sizes[0] == 50
+        # small runs do not get a head batch at all: a second launch costs
+        # more than the upload it would hide
+        engine.Config.head_min_bytes = 64 << 20
+        assert [len(b) for b in pipe.batches(range(100))] == [100]
     finally:
+        engine.Config.head_min_bytes = old_min
         engine.Config.cache_bytes, engine.Config.batch_bytes = old
 
 
