@@ -438,9 +438,11 @@ def oracle_check(job, cfg, u, kw):
     return bool(np.array_equal(r.count, want)), what
 
 
-def run_config(job, cfg, reps=4, warm=2, cpu_shape=False):
+def run_config(job, cfg, reps=None, warm=3, cpu_shape=False):
     """frames/s of one BASELINE configuration, resident and end to end,
     frame-sharded over the ranks"""
+    if reps is None:      # millisecond runs: more of them
+        reps = 20 if cfg in (1, 3) else 4
     from pmda_b200 import engine, synthetic
     from pmda_b200.rdf import InterRDF, InterRDF_s
     mode, n = CONFIG_FRAMES[cfg]

@@ -56,7 +56,9 @@ const char *rdfk_last_error(void);
 /* Cross-check switches for the test suite; 0 (the default) in production.
  * bit 0: no bounding-box pruning (every group pair is evaluated; hydrogen
  * bonds: no acceptor cell grid), bit 1: no one-shift-per-group arithmetic,
- * bit 2: no Euclidean refinement of the triclinic box test.  Results never
+ * bit 2: no Euclidean refinement of the triclinic box test, bits 8-11: number
+ * of slices the last work items of a launch are cut into (0 = the library's
+ * own rule).  Results never
  * depend on the flags, throughput does.  An explicit call on purpose -- not an
  * environment variable a production job could inherit.  Process-wide; returns
  * the previous flags.                                                        */
@@ -118,21 +120,6 @@ int rdfk_rdf_sites(const float *xyz, int F, int natoms, const int *idxA,
                    long long total_cells, int boxkind, const float *box,
                    double r0, double r1, int nbins, const double *edges,
                    unsigned int *count, void *stream);
-
-/* InterRDF_s epilogue (pmda/rdf.py:311-334) for the counts of n_blocks frame
- * blocks, count[b][i], i < n = cells * nbins:
- *   count_f64[b][i] = (double) count[b][i]        the float64 tensors the
- *                                                  reference returns per block
- *   total[i]        = sum_b count[b][i]           np.sum(self._results[:, 0])
- *   rdf[i]          = total[i] / den[i % nbins]   den = density*vol*n_frames or
- *                                                  vol*n_frames, computed by the
- *                                                  caller in the reference's
- *                                                  operation order
- * Any of the three outputs may be NULL.  The division is one IEEE double
- * division per element, as in numpy: same bits.                            */
-int rdfk_sites_finish(const unsigned int *count, int n_blocks, long long n,
-                      int nbins, const double *den, double *count_f64,
-                      double *total, double *rdf, void *stream);
 
 /* ------------------------------------------------------------------------
  * Contacts frame kernel (the sibling analysis on the same
@@ -242,6 +229,23 @@ int rdfk_host_gather_rows(const void *src_host, size_t n_frames,
                           const int *idx_host, size_t n_idx, float *dst_host,
                           int nthreads);
 
+/* InterRDF_s epilogue (pmda/rdf.py:311-334) on the HOST, threaded, for the
+ * counts of n_blocks frame blocks after their D2H copy, count[b][i],
+ * i < n = cells * nbins:
+ *   count_f64[b][i] = (double) count[b][i]        the float64 tensors the
+ *                                                  reference returns per block
+ *   total[i]        = sum_b count[b][i]           np.sum(self._results[:, 0])
+ *   rdf[i]          = total[i] / den[i % nbins]   den = density*vol*n_frames or
+ *                                                  vol*n_frames, computed by the
+ *                                                  caller in the reference's
+ *                                                  operation order
+ * Any of the three outputs may be NULL.  One IEEE double division per
+ * element, as in numpy: same bits.  All pointers are host memory.          */
+int rdfk_host_sites_finish(const unsigned int *count_host, int n_blocks,
+                           long long n, int nbins, const double *den_host,
+                           double *count_f64_host, double *total_host,
+                           double *rdf_host, int nthreads);
+
 /* ------------------------------------------------------------------------
  * Diagnostics / measurement helpers (not on the reference path).
  * ------------------------------------------------------------------------ */
@@ -260,6 +264,15 @@ int rdfk_host_gather_rows(const void *src_host, size_t n_frames,
  * the first violation.  Synchronises `stream`.                               */
 int rdfk_rdf_stats(const void *workspace, unsigned long long *out_host,
                    void *stream);
+
+/* The same 8 counters copied to DEVICE memory `out_device`, asynchronously on
+ * `stream` (for callers that fetch them together with the histograms).       */
+int rdfk_rdf_stats_async(const void *workspace, unsigned long long *out_device,
+                         void *stream);
+
+/* cudaMemsetAsync(dst, 0, nbytes) on `stream`: zero a result vector before
+ * the first accumulating call.                                               */
+int rdfk_zero_async(void *dst, size_t nbytes, void *stream);
 
 /* number of CUDA kernels this library has launched since it was loaded
  * (all streams, all devices); bench.py reports the difference over its timed

@@ -48,9 +48,10 @@ def _declare(L):
         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
         c_void_p, c_int, c_ll, c_int, c_void_p, c_double, c_double, c_int,
         c_void_p, c_void_p, c_void_p]
-    L.rdfk_sites_finish.restype = c_int
-    L.rdfk_sites_finish.argtypes = [c_void_p, c_int, c_ll, c_int, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_void_p]
+    L.rdfk_host_sites_finish.restype = c_int
+    L.rdfk_host_sites_finish.argtypes = [c_void_p, c_int, c_ll, c_int,
+                                         c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_int]
     L.rdfk_contacts.restype = c_int
     L.rdfk_contacts.argtypes = [
         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
@@ -74,6 +75,10 @@ def _declare(L):
     L.rdfk_rdf_stats.restype = c_int
     L.rdfk_rdf_stats.argtypes = [c_void_p, ctypes.POINTER(ctypes.c_ulonglong),
                                  c_void_p]
+    L.rdfk_rdf_stats_async.restype = c_int
+    L.rdfk_rdf_stats_async.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.rdfk_zero_async.restype = c_int
+    L.rdfk_zero_async.argtypes = [c_void_p, c_size_t, c_void_p]
     L.rdfk_launch_count.restype = ctypes.c_ulonglong
     L.rdfk_launch_count.argtypes = []
     L.rdfk_measure_fp32_peak.restype = c_int
@@ -84,11 +89,12 @@ def _declare(L):
 EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_set_debug_flags",
            "rdfk_build_has_checks", "rdfk_device_info",
            "rdfk_rdf_workspace_bytes", "rdfk_rdf_hist", "rdfk_rdf_sites",
-           "rdfk_sites_finish",
+           "rdfk_host_sites_finish",
            "rdfk_contacts", "rdfk_unpack_planes",
            "rdfk_hbonds_workspace_bytes", "rdfk_hbonds",
            "rdfk_host_hash64_rows", "rdfk_host_gather_rows",
-           "rdfk_rdf_stats", "rdfk_launch_count", "rdfk_measure_fp32_peak")
+           "rdfk_rdf_stats", "rdfk_rdf_stats_async", "rdfk_zero_async",
+           "rdfk_launch_count", "rdfk_measure_fp32_peak")
 
 
 def lib():
@@ -162,14 +168,32 @@ def rdf_sites(xyz, F, natoms, idx_a, idx_b, off_a, off_b, cell_off, n_sites,
         _ptr(count), ctypes.c_void_p(int(stream))))
 
 
-def sites_finish(count, n_blocks, n, nbins, den, count_f64, total, rdf,
-                 stream):
-    """rdfk_sites_finish: uint32 counts -> float64 per-block tensors, their
-    sum and the rdf (any output may be None)"""
-    check(lib().rdfk_sites_finish(
-        _ptr(count), int(n_blocks), int(n), int(nbins), _ptr(den),
-        _ptr(count_f64), _ptr(total), _ptr(rdf),
-        ctypes.c_void_p(int(stream))))
+def _np_ptr(a):
+    return None if a is None else \
+        ctypes.c_void_p(a.__array_interface__["data"][0])
+
+
+def host_sites_finish(count, nbins, den=None, want_total=False, nthreads=1):
+    """rdfk_host_sites_finish on numpy arrays: uint32/int32 ``count``
+    [n_blocks, n] -> (float64 [n_blocks, n], total [n] or None, rdf [n] or
+    None), fresh arrays.  Releases the GIL."""
+    import numpy as np
+    if count.dtype not in (np.uint32, np.int32) or count.ndim != 2 or \
+            not count.flags.c_contiguous:
+        raise ValueError("host_sites_finish: bad count array")
+    n_blocks, n = count.shape
+    out = np.empty((n_blocks, n), dtype=np.float64)
+    total = np.empty(n, dtype=np.float64) if want_total else None
+    rdf = None
+    if den is not None:
+        den = np.ascontiguousarray(den, dtype=np.float64)
+        if den.shape != (nbins,):
+            raise ValueError("host_sites_finish: den must have nbins entries")
+        rdf = np.empty(n, dtype=np.float64)
+    check(lib().rdfk_host_sites_finish(
+        _np_ptr(count), int(n_blocks), int(n), int(nbins), _np_ptr(den),
+        _np_ptr(out), _np_ptr(total), _np_ptr(rdf), int(nthreads)))
+    return out, total, rdf
 
 
 CONTACT_HARD, CONTACT_RADIUS, CONTACT_SOFT, CONTACT_DIST = 0, 1, 2, 3
@@ -255,6 +279,17 @@ def rdf_stats(workspace, stream):
             "tile_items": int(out[2]), "tile_pairs": int(out[3]),
             "wrapped_atoms": int(out[4]), "wrapped_frames": int(out[5]),
             "violations": int(out[6]), "first_violation": int(out[7])}
+
+
+def rdf_stats_async(workspace, out_dev, stream):
+    """the 8 workspace counters -> int64 device tensor `out_dev`, async"""
+    check(lib().rdfk_rdf_stats_async(_ptr(workspace), _ptr(out_dev),
+                                     ctypes.c_void_p(int(stream))))
+
+
+def zero_async(t, stream):
+    check(lib().rdfk_zero_async(_ptr(t), int(t.numel() * t.element_size()),
+                                ctypes.c_void_p(int(stream))))
 
 
 def set_debug_flags(flags):

@@ -84,7 +84,6 @@ static int set_err(int code, const char *fmt, const char *a = "",
 // compile-time shape of the tile kernel
 // ---------------------------------------------------------------------------
 constexpr int TPB = 256;         // threads per CTA (8 warps)
-constexpr int NWARP = TPB / 32;
 constexpr int RI = 4;            // i-atoms held in registers per lane
 constexpr int CI = 32 * RI;      // atoms per i-cluster (one warp work item)
 constexpr int GJ = 8;            // atoms per j-group (pruning granule)
@@ -1012,8 +1011,11 @@ struct PairArgs {
   int ncl_i, ncl_j, ngrp_j;
   int symmetric;      // gi == gj: circulant half of the cluster matrix
   int swapped;        // i side is the reference's g2 (`conf`), j side its g1
-  int total_items;    // F * ncl_i * nsplit
-  int nsplit;         // work items per (frame, i-cluster): slices of the j side
+  int total_items;    // work items: whole (frame, i-cluster) items first,
+                      // then the sliced ones
+  int whole_items;    // items [0, whole_items) are whole
+  int nslice;         // every later (frame, i-cluster) is cut into `nslice`
+                      // work items along its j-clusters
   const FrameParams *fparams;
   const float2 *tables;   // [F][2][nbins + 1]
   HistParams hp;
@@ -1305,9 +1307,16 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
     if (lane == 0) item = atomicAdd(&a.header->work_counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= a.total_items) break;
-    // small systems: a (frame, i-cluster) is cut into `nsplit` slices of its
-    // j-clusters so that every warp of the grid gets several items
-    const int slice = item % a.nsplit, fc = item / a.nsplit;
+    // The last few (frame, i-cluster) items of a launch would each keep one
+    // warp busy while the rest of the GPU idles (config 1: 2400 items for
+    // 2368 resident warps); they are cut into slices of their j-clusters.
+    int fc = item, slice = 0, nsl = 1;
+    if (item >= a.whole_items) {
+      const int v = item - a.whole_items;
+      nsl = a.nslice;
+      fc = a.whole_items + v / nsl;
+      slice = v - (v / nsl) * nsl;
+    }
     if (slice == 0) ++n_items;
     const int f = fc / a.ncl_i, ic = fc - f * a.ncl_i;
     const FrameParams *fp = a.fparams + f;
@@ -1728,8 +1737,8 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
     // 16 group boxes of two surviving clusters per round.  Surviving groups
     // of the current table class are staged into shared memory by cp.async
     // (each lane copies its own group) and evaluated one after the other.
-    // t0 .. t1: this slice's part of the j-clusters; `own`: the slice also
-    // takes my own cluster (symmetric schedule, slice 0)
+    // t0 .. t1: this work item's part of the j-clusters; `own`: it also takes
+    // my own cluster (symmetric schedule, slice 0)
     int nrounds, t0, t1, own = 0;
     if (a.symmetric) {
       // round 0: my own cluster in full (weight 1: both orders and the self
@@ -1737,12 +1746,12 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
       const int nt = a.ncl_i;
       int cnt = (nt - 1) / 2;
       if ((nt & 1) == 0 && ic < nt / 2) ++cnt;
-      t0 = (int)((long long)cnt * slice / a.nsplit);
-      t1 = (int)((long long)cnt * (slice + 1) / a.nsplit);
+      t0 = cnt * slice / nsl;
+      t1 = cnt * (slice + 1) / nsl;
       own = slice == 0 ? 1 : 0;
     } else {
-      t0 = (int)((long long)a.ncl_j * slice / a.nsplit);
-      t1 = (int)((long long)a.ncl_j * (slice + 1) / a.nsplit);
+      t0 = (int)((long long)a.ncl_j * slice / nsl);
+      t1 = (int)((long long)a.ncl_j * (slice + 1) / nsl);
     }
     nrounds = own + (t1 - t0 + 31) / 32;
     // which table classes occur in this frame
@@ -1974,31 +1983,6 @@ __global__ __launch_bounds__(256) void sites_kernel(
   }
   const int k = exact_bin<BOXKIND>(xa, ya, za, xb, yb, zb, &s_fp, &s_hp);
   if (k >= 0) atomicAdd(count + (size_t)cell * hp.nbins + k, 1u);
-}
-
-// ---------------------------------------------------------------------------
-// InterRDF_s epilogue on the device (pmda/rdf.py:311-334): the per-block
-// uint32 counts become the float64 tensors the reference returns
-// (`count[i][a, b, :]`, pmda/rdf.py:294-295), their sum over the blocks
-// (`np.sum(self._results[:, 0])`, exact: integers below 2^53) and
-//   rdf = count / den[bin],   den = density * vol * n_frames   (host, [nbins])
-// -- one IEEE double division per cell, the same operation numpy performs, so
-// the bits are numpy's.  One thread per (cell, bin).
-// ---------------------------------------------------------------------------
-__global__ __launch_bounds__(256) void sites_finish_kernel(
-    const unsigned int *__restrict__ count, int n_blocks, long long n, int nbins,
-    const double *__restrict__ den, double *__restrict__ count_f64,
-    double *__restrict__ total, double *__restrict__ rdf) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double sum = 0.0;
-  for (int b = 0; b < n_blocks; ++b) {
-    const double c = (double)count[(size_t)b * n + i];
-    if (count_f64) count_f64[(size_t)b * n + i] = c;
-    sum = __dadd_rn(sum, c);
-  }
-  if (total) total[i] = sum;
-  if (rdf) rdf[i] = __ddiv_rn(sum, den[i % nbins]);
 }
 
 // ---------------------------------------------------------------------------
@@ -2259,11 +2243,11 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   if (total > 0x7fff0000LL)
     return set_err(RDFK_EINVAL, "too many cluster work items in one call; "
                                 "pass fewer frames%s%s");
-  a.nsplit = 1;
-  a.total_items = (int)total;
+  a.total_items = a.whole_items = (int)total;
+  a.nslice = 1;
   a.fparams = fparams; a.tables = tables; a.hp = hp; a.hist = hist;
   a.header = header;
-  // warp-private histogram copies: all NWARP of them if two CTAs still fit on
+  // warp-private histogram copies: one per warp if two CTAs still fit on
   // an SM, otherwise as many as one CTA can hold, otherwise global atomics
   const size_t per_copy = ((size_t)hp.nbins + 1) * sizeof(unsigned int);
   const size_t tab_bytes = 2 * ((size_t)hp.nbins + 1) * sizeof(float2) + 16;
@@ -2311,19 +2295,25 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   }
   long long grid = (long long)sms * occ;
   {
-    // Small systems: with fewer than ~8 work items per resident warp the
-    // kernel's time is that of the unluckiest warp (config 1: 2400 items for
-    // 2368 warps, so 32 warps do two items while the rest idle).  Cut every
-    // item into slices of its j-clusters.
+    // Tail of a small launch: with `warps` resident warps the last
+    // total % warps items (all of them when total < warps) would run one per
+    // warp while the other warps have nothing left.  They are cut into up to
+    // 8 slices of their j-clusters.  (Slicing EVERY item of a small system
+    // was measured slower: each slice repeats the item's set-up and box
+    // tests.)  Debug flags bits 8-11 force the slice count for the tests.
     const long long warps = grid * NW;
+    const long long left = total % warps;
     const long long jparts = same_group ? (a.ncl_j - 1) / 2 : a.ncl_j;
-    long long ns = (8 * warps + total - 1) / total;
+    long long ns = left > 0 ? warps / left : 1;
     if (ns > 8) ns = 8;
+    if ((debug_flags >> 8) & 15) ns = (debug_flags >> 8) & 15;
     if (ns > jparts) ns = jparts;
     if (ns < 1) ns = 1;
-    if (total * ns > 0x7fff0000LL) ns = 1;
-    a.nsplit = (int)ns;
-    a.total_items = (int)(total * ns);
+    if (left > 0 && ns > 1) {
+      a.nslice = (int)ns;
+      a.whole_items = (int)(total - left);
+      a.total_items = (int)(total - left + left * ns);
+    }
   }
   const long long need = ((long long)a.total_items + NW - 1) / NW;
   if (grid > need) grid = need;
@@ -2442,28 +2432,6 @@ extern "C" int rdfk_rdf_sites(const float *xyz, int F, int natoms,
   return RDFK_OK;
 }
 
-extern "C" int rdfk_sites_finish(const unsigned int *count, int n_blocks,
-                                 long long n, int nbins, const double *den,
-                                 double *count_f64, double *total, double *rdf,
-                                 void *stream) {
-  if (n_blocks < 0 || n < 0 || nbins < 1)
-    return set_err(RDFK_EINVAL, "negative size or nbins < 1%s%s");
-  if (n == 0 || n_blocks == 0) return RDFK_OK;
-  if (!count || (rdf && !den) || (!count_f64 && !total && !rdf))
-    return set_err(RDFK_EINVAL, "null pointer argument%s%s");
-  if (n % nbins) return set_err(RDFK_EINVAL, "n is not a multiple of nbins%s%s");
-  int sms = 0;
-  int rc = check_device(&sms);
-  if (rc) return rc;
-  const long long blocks = (n + 255) / 256;
-  if (blocks > 0x7fffffffLL) return set_err(RDFK_EINVAL, "too many cells%s%s");
-  sites_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      count, n_blocks, n, nbins, den, count_f64, total, rdf);
-  COUNT_LAUNCH(1);
-  CUDA_TRY(cudaGetLastError());
-  return RDFK_OK;
-}
-
 extern "C" int rdfk_contacts(const float *xyz, int F, int natoms,
                              const int *idx_a, const int *idx_b,
                              const double *r0, int n_pairs, int method,
@@ -2533,6 +2501,28 @@ extern "C" int rdfk_unpack_planes(const void *raw, long long frame_stride,
       xyz);
   COUNT_LAUNCH(1);
   CUDA_TRY(cudaGetLastError());
+  return RDFK_OK;
+}
+
+// Plumbing for callers that keep a persistent result vector on the device:
+// zero it and append the workspace counters on the caller's stream, without a
+// round trip through their tensor library (each torch stream context costs
+// more than these calls).
+extern "C" int rdfk_zero_async(void *dst, size_t nbytes, void *stream) {
+  if (nbytes == 0) return RDFK_OK;
+  if (!dst) return set_err(RDFK_EINVAL, "null pointer argument%s%s");
+  CUDA_TRY(cudaMemsetAsync(dst, 0, nbytes, (cudaStream_t)stream));
+  return RDFK_OK;
+}
+
+extern "C" int rdfk_rdf_stats_async(const void *workspace,
+                                    unsigned long long *out_device,
+                                    void *stream) {
+  if (!workspace || !out_device)
+    return set_err(RDFK_EINVAL, "null pointer argument%s%s");
+  CUDA_TRY(cudaMemcpyAsync(out_device, workspace,
+                           8 * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return RDFK_OK;
 }
 

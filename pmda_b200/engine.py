@@ -34,6 +34,16 @@ from . import _cabi, mdamath
 from .util import make_balanced_slices
 
 
+#: host-side trace points (tools/probe_host_time.py): a list collects
+#: (label, perf_counter) pairs while it is installed here; None = off
+_trace = None
+
+
+def _tp(label):
+    if _trace is not None:
+        _trace.append((label, time.perf_counter()))
+
+
 class Config(object):
     #: raw frame bytes staged per batch (bigger = fewer launches)
     batch_bytes = int(os.environ.get("PMDA_B200_BATCH_BYTES", 128 << 20))
@@ -63,7 +73,7 @@ class Config(object):
     #: hash runs while the GPU already works on the cached copy)
     hash_threads = int(os.environ.get(
         "PMDA_B200_HASH_THREADS",
-        max(1, min(8, (os.cpu_count() or 1) //
+        max(1, min(16, (os.cpu_count() or 1) //
                    max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))))
 
 
@@ -96,7 +106,9 @@ class CudaBackend(object):
     hbonds = staticmethod(_cabi.hbonds)
     host_hash_rows = staticmethod(_cabi.host_hash_rows)
     host_gather_rows = staticmethod(_cabi.host_gather_rows)
-    sites_finish = staticmethod(_cabi.sites_finish)
+    host_sites_finish = staticmethod(_cabi.host_sites_finish)
+    rdf_stats_async = staticmethod(_cabi.rdf_stats_async)
+    zero_async = staticmethod(_cabi.zero_async)
 
 
 _backend = CudaBackend()
@@ -143,6 +155,8 @@ class _DeviceState(object):
         self.consts = OrderedDict()
         #: page-locked landing buffer of a run's results
         self.result_pin = None
+        #: the device side of it (int64, grows): [counters | results | extras]
+        self.result_dev = None
         if self.is_cuda:
             with torch.cuda.device(device):
                 self.copy_stream = torch.cuda.Stream(device)
@@ -158,6 +172,26 @@ class _DeviceState(object):
     @property
     def compute_stream(self):
         return self.compute_streams[self.cur]
+
+    def result_vector(self, n):
+        """zeroed int64 device vector of n elements for this run's results
+        (persistent storage; zeroed on the first compute stream)"""
+        if not self.is_cuda:
+            return torch.zeros(n, dtype=torch.int64)
+        buf = self.result_dev
+        if buf is None or buf.numel() < n:
+            if buf is not None:
+                for cs in self.compute_streams:
+                    buf.record_stream(cs)
+            self.result_dev = None
+            buf = self.result_dev = torch.empty(max(n, 4096),
+                                                dtype=torch.int64,
+                                                device=self.device)
+            # allocated on torch's current stream, used on ours from now on
+            torch.cuda.current_stream(self.device).synchronize()
+        res = buf[:n]
+        _backend.zero_async(res, self.compute_streams[0].cuda_stream)
+        return res
 
     # staging buffers are flat and only ever grow: analyses of different
     # shapes taking turns on a device must not re-allocate (page-locking
@@ -476,8 +510,34 @@ def _box_row(row):
     return hit
 
 
+_box_rows_cache = OrderedDict()
+
+
 def _box_rows(dims, n):
-    """per-frame (kind, box9, volume) with one host evaluation per distinct box"""
+    """per-frame (kind, box9, volume) with one host evaluation per distinct
+    box; whole batches are remembered by content (NVT runs ask for the same
+    rows again and again)"""
+    if dims is None:
+        key = n
+    else:
+        dims = np.ascontiguousarray(dims)
+        key = (n, dims.dtype.str, dims.tobytes()) if dims.nbytes <= 65536 \
+            else None
+    if key is not None:
+        hit = _box_rows_cache.get(key)
+        if hit is not None:
+            return hit
+    out = _box_rows_uncached(dims, n)
+    if key is not None:
+        for a in out:
+            a.setflags(write=False)
+        _box_rows_cache[key] = out
+        while len(_box_rows_cache) > 64:
+            _box_rows_cache.popitem(last=False)
+    return out
+
+
+def _box_rows_uncached(dims, n):
     kinds = np.zeros(n, dtype=np.int32)
     box9 = np.zeros((n, 9), dtype=np.float32)
     vols = np.zeros(n, dtype=np.float64)
@@ -901,15 +961,16 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
     }
     with st.lock:
         cuda = st.is_cuda
-        ctx = torch.cuda.device(device) if cuda else _nullctx()
+        ctx = torch.cuda.device(device) if (
+            cuda and torch.cuda.current_device() != device.index) \
+            else _nullctx()
         with ctx:
             n_streams = max(1, min(2, Config.compute_streams)) if cuda else 1
             st.cur = 0
             cs = st.compute_streams
-            with (torch.cuda.stream(cs[0]) if cuda else _nullctx()):
-                res = torch.zeros(16 + n_blocks * nbins + n_extra,
-                                  dtype=torch.int64, device=device)
+            res = st.result_vector(16 + n_blocks * nbins + n_extra)
             hist = res[16:16 + n_blocks * nbins].view(n_blocks, nbins)
+            _tp("part: result buffer")
             edges_d = _dev_const(st, edges, np.float64)
             i1 = _dev_const(st, idx1, np.int32)
             i2 = i1 if same_group else _dev_const(st, idx2, np.int32)
@@ -920,6 +981,7 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
             timers = out["timers"]
             if cuda and n_streams > 1:
                 cs[1].wait_stream(cs[0])          # the zero-fill of `res`
+            _tp("part: constants, pipeline")
             n_batch = 0
             for (b, pos0, frames) in segs:
                 done = 0
@@ -929,6 +991,7 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     n_batch += 1
                     ws = st.get_workspace(ws_bytes)
                     xyz, dims, t_io, slot = pipe.fetch(batch)
+                    _tp("part: fetch")
                     kinds, box9, vols = _box_rows(dims, B)
                     lo_f = pos0 + done
                     out["vol"][lo_f:lo_f + B] = vols
@@ -936,6 +999,7 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     box_d = _dev_const(st, box9, np.float32)
                     out["first_launch"][b] = min(out["first_launch"][b],
                                                  time.time())
+                    _tp("part: box rows")
                     tm = _Timer(st)
                     tm.start()
                     stream = st.compute_stream.cuda_stream if cuda else 0
@@ -945,6 +1009,7 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                                     rng[0], rng[1], nbins, edges_d, excl,
                                     hist[b], ws, stream)
                     tm.stop()
+                    _tp("part: rdfk_rdf_hist (launches)")
                     pipe.mark_compute_done(slot)
                     timers.append((tm, lo_f, B))
                     done += B
@@ -954,14 +1019,13 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                 for k in range(min(n_streams, n_batch)):
                     ws_k = st.workspaces[k]
                     off = (-ws_k.data_ptr()) % 256
-                    with torch.cuda.stream(cs[k]):
-                        res[8 * k:8 * k + 8].copy_(
-                            ws_k[off:off + 64].view(torch.int64),
-                            non_blocking=True)
+                    be.rdf_stats_async(ws_k[off:], res[8 * k:8 * k + 8],
+                                       cs[k].cuda_stream)
                 if n_streams > 1 and n_batch > 1:
                     cs[0].wait_stream(cs[1])      # cs[0] now ends the run
             st.cur = 0
             out["res"], out["pipe"] = res, pipe
+            _tp("part: counters queued")
     return out
 
 
@@ -1075,6 +1139,13 @@ def _shard_for_this_rank(blocks, devices):
     and the number of frames in the run."""
     world, rank = _dist_world(), _dist_rank()
     n_frames = sum(len(b) for b in blocks)
+    if world == 1 and len(devices) == 1:      # everything is here
+        segs, pos = [], 0
+        for b, blk in enumerate(blocks):
+            if len(blk):
+                segs.append((b, pos, blk))
+            pos += len(blk)
+        return [segs], n_frames
     mine = _frame_shards(blocks, world)[rank]
     # second level: this rank's frames over its local devices
     sub_blocks = [f for (_, _, f) in mine]
@@ -1128,6 +1199,7 @@ def _local_parts(fn, devices, parts, fetch_now):
             for o in outs:
                 if o["st"].is_cuda:
                     o["st"].compute_streams[0].synchronize()
+        _tp("local: device finished")
         try:
             for o in outs:
                 with o["st"].lock:
@@ -1203,8 +1275,10 @@ def run_rdf_blocks(traj, natoms, idx1, idx2, same_group, blocks, nbins, rng,
                              idx1, idx2, same_group, nbins, rng, edges, excl,
                              n_extra)
 
+    _tp("blocks: sharding")
     outs, host = _local_parts(fn, devices, parts,
                               fetch_now=(world == 1 and len(devices) == 1))
+    _tp("blocks: wait for the device, verify, timers")
     main, extra, stats = _exchange(outs, host, n_blocks * nbins, n_frames)
     if stats:
         _check_stats(outs[0]["st"], stats)
@@ -1217,123 +1291,204 @@ def run_rdf_blocks(traj, natoms, idx1, idx2, same_group, blocks, nbins, rng,
         r[1] = np.array(vol, dtype=np.float64)
         return r
 
-    return _finish(hist_np, extra[0], extra[1], extra[2], first, blocks,
-                   make_result)
+    res = _finish(hist_np, extra[0], extra[1], extra[2], first, blocks,
+                  make_result)
+    _tp("blocks: results assembled")
+    return res
+
+
+def _site_gather(site, natoms):
+    """The atoms the site pairs reference, sorted and unique, and the site
+    index lists re-expressed as positions in that list -- or (None, idx_a,
+    idx_b) when most of the frame is referenced anyway.  The reference
+    gathers ``ag.positions`` first as well (pmda/rdf.py:296-301).  Kept in
+    the site description: computed once per analysis object."""
+    hit = site.get("_gather")
+    if hit is not None and hit[0] == natoms:
+        return hit[1]
+    idx_a = np.asarray(site["idx_a"], dtype=np.int64)
+    idx_b = np.asarray(site["idx_b"], dtype=np.int64)
+    both = np.concatenate([idx_a, idx_b])
+    if len(both) and (both.min() < 0 or both.max() >= natoms):
+        raise IndexError("site atom index out of range")
+    mark = np.zeros(natoms, dtype=bool)
+    mark[both] = True
+    used = np.flatnonzero(mark)
+    if len(used) == 0 or 2 * len(used) > natoms:
+        out = (None, idx_a, idx_b)
+    else:
+        where = np.empty(natoms, dtype=np.int32)
+        where[used] = np.arange(len(used), dtype=np.int32)
+        out = (used.astype(np.int32), where[idx_a], where[idx_b])
+    site["_gather"] = (natoms, out)
+    return out
 
 
 def _run_sites_part(device, traj, natoms, segs, n_blocks, n_frames, site,
                     nbins, rng, edges):
+    """All frames of one local device; like _run_rdf_part nothing here waits
+    for the GPU.  ``res``: device int32 ``[n_blocks, total_cells * nbins]``."""
     st = _state(device)
     be = _backend
     total_cells = int(site["cell_off"][-1])
     out = {
-        "hist": None,
+        "res": None, "timers": [], "pipe": None, "st": st,
         "vol": np.zeros(n_frames, dtype=np.float64),
         "io": np.zeros(n_frames, dtype=np.float64),
         "compute": np.zeros(n_frames, dtype=np.float64),
         "first_launch": np.full(n_blocks, np.inf),
     }
+    gather, idx_a, idx_b = _site_gather(site, natoms)
     with st.lock:
         cuda = st.is_cuda
         ctx = torch.cuda.device(device) if cuda else _nullctx()
         with ctx:
-            count = torch.zeros((n_blocks, total_cells * nbins),
-                                dtype=torch.int32, device=device)
-            edges_d = torch.as_tensor(edges, dtype=torch.float64,
-                                      device=device)
-            ia = _to_dev_i32(site["idx_a"], device)
-            ib = _to_dev_i32(site["idx_b"], device)
-            oa = _to_dev_i32(site["off_a"], device)
-            ob = _to_dev_i32(site["off_b"], device)
-            co = torch.as_tensor(np.asarray(site["cell_off"], dtype=np.int64),
-                                 device=device)
-            pipe = _Pipeline(st, traj, natoms)
-            timers = []
+            st.cur = 0
+            cs0 = st.compute_streams[0]
+            with (torch.cuda.stream(cs0) if cuda else _nullctx()):
+                count = torch.zeros((n_blocks, total_cells * nbins),
+                                    dtype=torch.int32, device=device)
+            edges_d = _dev_const(st, edges, np.float64)
+            # the four int32 index lists travel (and are looked up) as one
+            na, nb_, ns1 = len(idx_a), len(idx_b), len(site["off_a"])
+            packed = _dev_const(st, np.concatenate(
+                [idx_a, idx_b, site["off_a"], site["off_b"]]), np.int32)
+            ia, ib = packed[:na], packed[na:na + nb_]
+            oa = packed[na + nb_:na + nb_ + ns1]
+            ob = packed[na + nb_ + ns1:]
+            co = _dev_const(st, site["cell_off"], np.int64)
+            pipe = _Pipeline(st, traj, natoms, gather=gather)
+            timers = out["timers"]
+            _tp("part: constants, pipeline")
             for (b, pos0, frames) in segs:
                 done = 0
                 for batch in pipe.batches(frames):
                     B = len(batch)
                     xyz, dims, t_io, slot = pipe.fetch(batch)
+                    _tp("part: fetch")
                     kinds, box9, vols = _box_rows(dims, B)
                     lo_f = pos0 + done
                     out["vol"][lo_f:lo_f + B] = vols
                     out["io"][lo_f:lo_f + B] = t_io / B
-                    # allocated and filled on the batch's compute stream: the
-                    # host runs batches ahead of the device, and a block freed
-                    # on another stream could be handed out again (and
-                    # overwritten) while this batch's kernels still wait
-                    with (torch.cuda.stream(st.compute_stream) if cuda
-                          else _nullctx()):
-                        box_d = torch.as_tensor(box9, device=device)
-                    if cuda:
-                        st.compute_stream.wait_stream(
-                            torch.cuda.current_stream(device))
+                    box_d = _dev_const(st, box9, np.float32)
                     out["first_launch"][b] = min(out["first_launch"][b],
                                                  time.time())
+                    _tp("part: box rows")
                     tm = _Timer(st)
                     tm.start()
-                    stream = st.compute_stream.cuda_stream if cuda else 0
+                    stream = cs0.cuda_stream if cuda else 0
                     for kind, lo, hi in _runs(kinds):
-                        be.rdf_sites(xyz[lo:hi], hi - lo, natoms, ia, ib, oa,
-                                     ob, co, site["n_sites"], total_cells,
+                        be.rdf_sites(xyz[lo:hi], hi - lo, pipe.natoms, ia, ib,
+                                     oa, ob, co, site["n_sites"], total_cells,
                                      kind, box_d[lo:hi], rng[0], rng[1], nbins,
                                      edges_d, count[b], stream)
                     tm.stop()
                     pipe.mark_compute_done(slot)
+                    _tp("part: rdfk_rdf_sites (launch)")
                     timers.append((tm, lo_f, B))
                     done += B
-            for tm, lo_f, B in timers:
-                out["compute"][lo_f:lo_f + B] = tm.seconds() / B
-            if cuda:
-                st.sync_compute()
-            pipe.verify()       # cache hits still match the trajectory?
-            out["hist"] = count
+            out["res"], out["pipe"] = count, pipe
     return out
 
 
-def run_rdf_s_blocks(traj, natoms, site, blocks, nbins, rng, edges, n_jobs):
+def run_rdf_s_blocks(traj, natoms, site, blocks, nbins, rng, edges, n_jobs,
+                     den_fn=None):
     """InterRDF_s over frame blocks.  ``site`` holds the CSR description of
     the site pairs (see rdf.InterRDF_s).  The first element of every block
     tuple is ``np.array([<object array of n float64 [n1,n2,nbins]>, volume])``
-    like pmda/rdf.py:309 accumulated by :362-372."""
+    like pmda/rdf.py:309 accumulated by :362-372.
+
+    The float64 tensors are made from the int32 device counts by one threaded
+    native pass (rdfk_host_sites_finish).  With ``den_fn`` (maps the list of
+    per-block volumes to the rdf denominator ``[nbins]``, in the reference's
+    own operation order) that pass also sums the blocks and divides:
+    -> ``(per-block tuples, {"count": [...], "rdf": [...], "den": den})``.
+    """
     devices = _backend.devices(n_jobs)
     n_blocks = len(blocks)
     total_cells = int(site["cell_off"][-1])
+    n = total_cells * nbins
     parts, n_frames = _shard_for_this_rank(blocks, devices)
+    world = _dist_world()
 
     def fn(device, segs):
         return _run_sites_part(device, traj, natoms, segs, n_blocks, n_frames,
                                site, nbins, rng, edges)
 
-    outs = _run_parts(fn, devices, parts)
-    cnt = _combine(outs, devices[0], n_blocks, total_cells * nbins,
-                   torch.int32)
-    cnt = _allreduce(cnt)
+    _tp("blocks: sharding")
+    outs, _ = _local_parts(fn, devices, parts, fetch_now=False)
+    _tp("blocks: parts queued and finished on the device")
+    st = outs[0]["st"]
+    cnt = outs[0]["res"]
+    for o in outs[1:]:                  # other local devices
+        cnt = cnt + o["res"].to(cnt.device)
     extra = np.stack([sum(o["vol"] for o in outs),
                       sum(o["io"] for o in outs),
                       sum(o["compute"] for o in outs)])
-    if _dist_world() > 1:
+    if world > 1:
+        cnt = _allreduce(cnt)
         extra = _allreduce(torch.from_numpy(extra)).numpy()
     first = np.min(np.stack([o["first_launch"] for o in outs]), axis=0)
-    cnt_np = cnt.cpu().numpy()
+
+    # per-block volumes, summed in frame order like `res += r`
+    vols, pos = [], 0
+    for blk in blocks:
+        v = 0.0
+        for x in extra[0][pos:pos + len(blk)]:
+            v = v + float(x)
+        vols.append(np.array(np.float64(v)))
+        pos += len(blk)
+    den = None if den_fn is None else np.ascontiguousarray(den_fn(vols),
+                                                           dtype=np.float64)
+    # epilogue: the int32 counts come to the host in one D2H copy; the
+    # float64 tensors the reference returns, their sum over the blocks and
+    # the rdf are made from them by the threaded native pass
+    # (rdfk_host_sites_finish: 3x fewer PCIe bytes than shipping float64, and
+    # the results are ordinary numpy arrays the caller may keep)
+    want_total = den is not None and n_blocks > 1
+    with st.lock:
+        if st.is_cuda:
+            with torch.cuda.device(st.device):
+                flat = cnt.reshape(-1)
+                even = flat.numel() % 2 == 0
+                cnt_host = _result_to_host(
+                    st, flat.view(torch.int64) if even
+                    else flat.to(torch.int64), st.compute_streams[0])
+                cnt_host = cnt_host.view(np.int32) if even \
+                    else cnt_host.astype(np.int32)
+        else:
+            cnt_host = cnt.numpy()
+        cnt_host = np.ascontiguousarray(cnt_host).reshape(n_blocks, n)
+        _tp("blocks: counts on the host")
+        host, total, rdf_flat = _backend.host_sites_finish(
+            cnt_host, nbins, den, want_total, Config.gather_threads)
+        _tp("blocks: native epilogue")
     cell_off = np.asarray(site["cell_off"], dtype=np.int64)
     shapes = site["shapes"]
 
-    def make_result(b, flat, vol):
+    def per_site_views(flat):
+        dense = flat.reshape(total_cells, nbins)
         per_site = np.empty(len(shapes), dtype=object)
-        # one conversion for all sites; the per-site tensors are disjoint
-        # slices of it
-        dense = flat.reshape(total_cells, nbins).astype(np.float64)
-        for s, (n1, n2) in enumerate(shapes):
-            per_site[s] = dense[cell_off[s]:cell_off[s + 1]].reshape(
+        for s_, (n1, n2) in enumerate(shapes):
+            per_site[s_] = dense[cell_off[s_]:cell_off[s_ + 1]].reshape(
                 n1, n2, nbins)
+        return per_site
+
+    def make_result(b, flat, vol):
         r = np.empty(2, dtype=object)
-        r[0] = per_site
+        r[0] = per_site_views(flat)
         r[1] = np.array(vol, dtype=np.float64)
         return r
 
-    return _finish(cnt_np, extra[0], extra[1], extra[2], first, blocks,
-                   make_result)
+    res = _finish(host, extra[0], extra[1], extra[2], first, blocks,
+                  make_result)
+    _tp("blocks: results assembled")
+    if den is None:
+        return res
+    if not want_total:
+        total = host[0]          # one block: the sum is the block itself
+    return res, {"count": per_site_views(total),
+                 "rdf": list(per_site_views(rdf_flat)), "den": den}
 
 
 # --------------------------------------------------------------------------

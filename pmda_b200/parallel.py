@@ -28,6 +28,11 @@ import numpy as np
 from .util import timeit, make_balanced_slices
 
 
+def _tp(label):
+    from . import engine
+    engine._tp(label)
+
+
 class Timing(object):
     """Timings gathered during ``run()`` (pmda/parallel.py:33-104).
 
@@ -158,6 +163,7 @@ class ParallelAnalysisBase(object):
         slices = make_balanced_slices(n_frames, n_blocks,
                                       start=start, stop=stop, step=step)
 
+        _tp("run: slices")
         with timeit() as total:
             with timeit() as prepare:
                 self._prepare()
@@ -167,7 +173,9 @@ class ParallelAnalysisBase(object):
                 wait_start = time.time()
                 device_blocks = getattr(self, '_device_blocks', None)
                 if device_blocks is not None and len(_blocks):
+                    _tp("run: prepare")
                     res = device_blocks(_blocks, n_jobs)
+                    _tp("run: device blocks returned")
                 else:
                     res = [self._block_helper(b) for b in _blocks]
             if len(res) == 0:
@@ -177,6 +185,7 @@ class ParallelAnalysisBase(object):
                 self._results = _stack_block_results([el[0] for el in res])
                 self._blocks = _blocks
                 self._conclude()
+        _tp("run: conclude")
         self.timing = Timing(
             np.hstack([el[1] for el in res]),
             np.hstack([el[2] for el in res]), total.elapsed,
@@ -185,6 +194,7 @@ class ParallelAnalysisBase(object):
             np.array([el[4] - wait_start for el in res]),
             np.array([el[5] for el in res]),
             np.array([el[6] for el in res]))
+        _tp("run: timing object")
         return self
 
     def _block_helper(self, frames):

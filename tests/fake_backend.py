@@ -81,6 +81,17 @@ class OracleBackend(object):
                                        int(nbins), e, view)
         count += torch.from_numpy(dense.reshape(-1).astype(np.int32))
 
+    @staticmethod
+    def host_gather_rows(src, idx, dst, nthreads=1):
+        from pmda_b200 import _cabi          # host code of the product library
+        return _cabi.host_gather_rows(src, idx, dst, nthreads)
+
+    @staticmethod
+    def host_sites_finish(count, nbins, den=None, want_total=False,
+                          nthreads=1):
+        from pmda_b200 import _cabi          # host code of the product library
+        return _cabi.host_sites_finish(count, nbins, den, want_total, nthreads)
+
     def contacts(self, xyz, F, natoms, idx_a, idx_b, r0, n_pairs, method,
                  radius, beta, lam, out, out_stride, stream):
         self.calls += 1

@@ -255,3 +255,29 @@ def test_large_coordinate_offsets_and_anisotropic_boxes():
     pos = synthetic.uniform_triclinic(2, 4000, dims, rng)
     u = Universe(pos, dims)
     _check_all_modes(u, u.atoms, u.atoms, rng=(0.0, 11.0))
+
+
+def test_sliced_tail_work_items_do_not_change_the_counts():
+    """the last work items of a launch (here: all of them, the systems are
+    small) are cut into slices of their j-clusters; debug flags bits 8-11
+    force the slice count"""
+    rng = np.random.default_rng(99)
+    L = 36.0
+    pos = (rng.random((5, 2100, 3)) * L).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    want, _, _ = oracle_interrdf(u, u.atoms, u.atoms, 60, (0.0, 13.0))
+    want2, _, _ = oracle_interrdf(u, u.atoms[:300], u.atoms[300:], 60, (0.0, 13.0))
+    dims = [30.0, 31.0, 32.0, 70.0, 80.0, 65.0]
+    ut = Universe(synthetic.uniform_triclinic(3, 1500, dims, rng), dims)
+    want3, _, _ = oracle_interrdf(ut, ut.atoms, ut.atoms, 50, (0.0, 11.0))
+    for ns in (0, 1, 2, 3, 5, 8, 15):
+        flags = ns << 8
+        np.testing.assert_array_equal(
+            _gpu(u, u.atoms, u.atoms, 60, (0.0, 13.0), debug=flags), want)
+        np.testing.assert_array_equal(
+            _gpu(u, u.atoms[:300], u.atoms[300:], 60, (0.0, 13.0), debug=flags),
+            want2)
+        np.testing.assert_array_equal(
+            _gpu(ut, ut.atoms, ut.atoms, 50, (0.0, 11.0), debug=flags | 3), want3)
+        np.testing.assert_array_equal(
+            _gpu(ut, ut.atoms, ut.atoms, 50, (0.0, 11.0), debug=flags), want3)

@@ -279,3 +279,22 @@ def test_rdf_s_conclude_against_reference_golden():
             assert np.array_equal(obj.count[s], z[pre + "count%d" % s])
             assert np.array_equal(obj.rdf[s], z[pre + "rdf%d" % s])
             assert np.array_equal(obj.cdf[s], z[pre + "cdf%d" % s])
+
+
+def test_bin_edges_are_numpy_histogram_edges():
+    """the fast path for the edges must give np.histogram's bits"""
+    from pmda_b200.rdf import _histogram_edges
+    rng = np.random.default_rng(0)
+    cases = [(75, (0.0, 15.0)), (200, (0.0, 15.0)), (1, (0, 1)), (412, (1.5, 9.25)),
+             (75, (np.float32(0.1), np.float64(7.3))), (7, (0, 7)), (3, [0.0, 1.0])]
+    for _ in range(300):
+        a, b = sorted(rng.random(2) * rng.choice([1.0, 10.0, 1e3, 1e-3]))
+        if a < b:
+            cases.append((int(rng.integers(1, 3000)), (float(a), float(b))))
+    for bins, r in cases:
+        want = np.histogram([-1], bins=bins, range=r)[1]
+        got = _histogram_edges({'bins': bins, 'range': r})
+        assert got.dtype == want.dtype and np.array_equal(got, want), (bins, r)
+    # odd settings go through numpy itself
+    for st in ({'bins': 5, 'range': (2.0, 2.0)}, {'bins': [0.0, 1.0, 4.0], 'range': (0.0, 4.0)}):
+        assert np.array_equal(_histogram_edges(st), np.histogram([-1], **st)[1])

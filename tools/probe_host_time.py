@@ -1,9 +1,8 @@
-"""Where does run() spend host time on the small configurations?  cProfile of
-repeated run()s (BASELINE configs[0] and [2]), resident and end to end."""
-import cProfile
-import io
+"""Where does run() spend host time on the small configurations?  Trace
+points of the engine (engine._trace) averaged over repeated run()s of
+BASELINE configs[0] and [2], resident and end to end."""
+import collections
 import os
-import pstats
 import sys
 import time
 
@@ -36,18 +35,26 @@ def main():
                 r = make().run()
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / reps
-            print("cfg%d cache=%s: run() %.3f ms, kernels %.3f ms, %d frames/s"
-                  % (cfg, bool(cache), dt * 1e3,
-                     1e3 * float(r.timing.compute.sum()), nf / dt), flush=True)
-            pr = cProfile.Profile()
-            pr.enable()
+            print("cfg%d cache=%s: make().run() %.3f ms, kernels %.3f ms, "
+                  "%d frames/s" % (cfg, bool(cache), dt * 1e3,
+                                   1e3 * float(r.timing.compute.sum()),
+                                   nf / dt), flush=True)
+            acc = collections.OrderedDict()
             for _ in range(reps):
-                make().run()
-            pr.disable()
-            s = io.StringIO()
-            pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
-            print("\n".join(l for l in s.getvalue().splitlines()
-                            if l.strip())[:6000], flush=True)
+                engine._trace = tr = []
+                t_a = time.perf_counter()
+                a = make()
+                tr.append(("analysis object", time.perf_counter()))
+                a.run()
+                engine._trace = None
+                prev = t_a
+                for label, t in tr:
+                    acc[label] = acc.get(label, 0.0) + (t - prev)
+                    prev = t
+            for label, v in acc.items():
+                print("    %-48s %7.1f us" % (label, 1e6 * v / reps))
+            print("    %-48s %7.1f us" % ("(sum)", 1e6 * sum(acc.values()) / reps),
+                  flush=True)
 
 
 if __name__ == "__main__":
