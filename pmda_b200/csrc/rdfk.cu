@@ -644,7 +644,8 @@ __global__ void params_kernel(int boxkind, const float *__restrict__ box,
                              fabs((double)b[4]) + fabs((double)b[7]),
                              fabs((double)b[8])};
       for (int k = 0; k < 3; ++k)
-        dk[k] += EPS32 * (2.0 * col[k] + A[k] + 2.0 * R + X[k]) * 1.01;
+        dk[k] = fmax(dk[k],
+                     EPS32 * (2.0 * col[k] + A[k] + 2.0 * R + X[k]) * 1.01);
     }
     if (boxkind == RDFK_BOX_ORTHO) {
       for (int k = 0; k < 3; ++k) {
@@ -1091,6 +1092,7 @@ struct Lay {
   static constexpr int OFF_IAT = OFF_CTX + SM_CTX;
   static constexpr int SM_WARP = OFF_IAT + SM_IAT;
   static constexpr int SM_FIXED = NW * SM_WARP;
+  static constexpr int NONPLAIN_UNROLL = TRI ? 1 : RI;
   static_assert(NTHR % 32 == 0 && NW >= 1 && NW <= 8, "1..8 warps per CTA");
   static_assert(QS >= PAIRS_PER_GROUP + GJ, "queue must absorb one group");
   static_assert(QS <= QS_MAX && QS % DWK == 0,
@@ -1400,7 +1402,43 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
              __fmul_rn(rprune, rprune);
     };
     // which of my quarters can reach group box `at`
-    auto quarter_mask = [&](const float *bb, int count, int at) -> int {
+    auto quarter_mask = [&](const float *bb, int count, int at, int code) -> int {
+      if (BOXKIND == RDFK_BOX_TRI && refine && (code & CODE_PLAIN)) {
+        // The group will be evaluated under the ONE lattice image its code
+        // names (that image is the minimum image of every pair of cluster and
+        // group that can be in range): a quarter can reach the group iff the
+        // Cartesian boxes, under that image, are within range.  This is the
+        // common case; it needs neither the fractional test nor the search
+        // for the reachable image below.
+        const float nx = (float)((code & 3) - 1),
+                    ny = (float)(((code >> 2) & 3) - 1),
+                    nz = (float)(((code >> 4) & 3) - 1);
+        float sh[3];
+        sh[0] = __fmaf_rn(nz, ctx[17], __fmaf_rn(ny, ctx[15], __fmul_rn(nx, ctx[14])));
+        sh[1] = __fmaf_rn(nz, ctx[18], __fmul_rn(ny, ctx[16]));
+        sh[2] = __fmul_rn(nz, ctx[19]);
+        float cc[3], hc[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          cc[k] = __fsub_rn(gcj[(size_t)k * count + at], sh[k]);
+          hc[k] = gcj[(size_t)(3 + k) * count + at];
+        }
+        const float r2max = __fmul_rn(rprune, rprune);
+        int m = 0;
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          float e2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float ge = fmaxf(
+                0.f, __fsub_rn(fabsf(__fsub_rn(cc[k], qb[24 + k * 4 + r])),
+                               __fadd_rn(hc[k], qb[24 + (3 + k) * 4 + r])));
+            e2 = __fmaf_rn(ge, ge, e2);
+          }
+          m |= (e2 <= r2max) ? (1 << r) : 0;
+        }
+        return m;
+      }
       float cj[3], hj[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -1711,7 +1749,10 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
         const float xj8[GJ] = {Xa.x, Xa.y, Xa.z, Xa.w, Xb.x, Xb.y, Xb.z, Xb.w};
         const float yj8[GJ] = {Ya.x, Ya.y, Ya.z, Ya.w, Yb.x, Yb.y, Yb.z, Yb.w};
         const float zj8[GJ] = {Za.x, Za.y, Za.z, Za.w, Zb.x, Zb.y, Zb.z, Zb.w};
-#pragma unroll
+        // (triclinic: one copy of the quarter body -- 8 brick reductions --
+        // instead of four; this path is rare there and the instantiation is
+        // instruction-cache bound)
+#pragma unroll(L::NONPLAIN_UNROLL)
         for (int r = 0; r < RI; ++r) {
           if (!((qmask >> r) & 1)) continue;
           const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
@@ -1804,7 +1845,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           bool gpass = gv && box_test(gbj, a.ngrp_j, g, code);
           if (!all_slow) gpass = gpass && code_class(code) == cls;
           if (gpass) {
-            qmask = quarter_mask(gbj, a.ngrp_j, g);
+            qmask = quarter_mask(gbj, a.ngrp_j, g, code);
             gpass = qmask != 0;
           }
           const unsigned int gmask = __ballot_sync(0xffffffffu, gpass);

@@ -482,7 +482,8 @@ def _dev_const(st, arr, dtype):
     if hit is not None:
         st.consts.move_to_end(key)
         return hit
-    t = torch.as_tensor(a, device=st.device)
+    t = torch.as_tensor(a if a.flags.writeable else a.copy(),
+                        device=st.device)
     if st.is_cuda:
         # uploaded on torch's current stream; every later user runs on a
         # compute stream
