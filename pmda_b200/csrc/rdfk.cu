@@ -83,7 +83,6 @@ static int set_err(int code, const char *fmt, const char *a = "",
 // ---------------------------------------------------------------------------
 // compile-time shape of the tile kernel
 // ---------------------------------------------------------------------------
-constexpr int TPB = 256;         // threads per CTA (8 warps)
 constexpr int RI = 4;            // i-atoms held in registers per lane
 constexpr int CI = 32 * RI;      // atoms per i-cluster (one warp work item)
 constexpr int GJ = 8;            // atoms per j-group (pruning granule)
@@ -1048,13 +1047,26 @@ constexpr int QS_MAX = 64;    // queue slots per lane (fail mask is 64 bits)
 #ifndef RDFK_QS_TRI
 #define RDFK_QS_TRI ((RDFK_IAT_SMEM_TRI && RDFK_TPB_TRI == 256) ? 56 : 64)
 #endif
+// ... and of the other two (orthorhombic, no box)
+#ifndef RDFK_TPB_ORTHO
+#define RDFK_TPB_ORTHO 256
+#endif
+#ifndef RDFK_IAT_SMEM_ORTHO
+#define RDFK_IAT_SMEM_ORTHO 0
+#endif
+#ifndef RDFK_QS_ORTHO
+#define RDFK_QS_ORTHO ((RDFK_IAT_SMEM_ORTHO && RDFK_TPB_ORTHO == 256) ? 56 : 64)
+#endif
 constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
 constexpr int NSTAGE = 32;    // staged j-groups per warp (one test round)
 constexpr int PAIRS_PER_GROUP = GJ * RI;   // per lane
 constexpr int DW = 16;        // queue entries per lane in flight in the drain
 // (the triclinic instantiation is instruction-cache bound: a narrower loop
 // is 9 % faster there, 16 vs 8 is a wash for the others)
-constexpr int DW_TRI = 8;
+#ifndef RDFK_DW_TRI
+#define RDFK_DW_TRI 8
+#endif
+constexpr int DW_TRI = RDFK_DW_TRI;
 
 constexpr int SM_ST = NSTAGE * 3 * GJ * 4;     // staged j-groups
 constexpr int SM_CODE = NSTAGE * 4;            // their (group, code, quarter mask)
@@ -1075,10 +1087,11 @@ constexpr int SM_CTX = 32 * 4;                 // per-item constants of the box 
 template <int BOXKIND>
 struct Lay {
   static constexpr bool TRI = BOXKIND == RDFK_BOX_TRI;
-  static constexpr int NTHR = TRI ? RDFK_TPB_TRI : TPB;   // threads per CTA
+  static constexpr int NTHR = TRI ? RDFK_TPB_TRI : RDFK_TPB_ORTHO;  // per CTA
   static constexpr int NW = NTHR / 32;                    // warps per CTA
-  static constexpr bool IAT_SMEM = TRI && RDFK_IAT_SMEM_TRI;
-  static constexpr int QS = TRI ? RDFK_QS_TRI : QS_MAX;
+  static constexpr bool IAT_SMEM =
+      TRI ? (RDFK_IAT_SMEM_TRI != 0) : (RDFK_IAT_SMEM_ORTHO != 0);
+  static constexpr int QS = TRI ? RDFK_QS_TRI : RDFK_QS_ORTHO;
   static constexpr int DWK = BOXKIND == RDFK_BOX_TRI ? DW_TRI : DW;
   static constexpr int SM_Q = QS * 32 * 4;      // bytes per warp: queue
   static constexpr int SM_IAT = IAT_SMEM ? 3 * CI * 4 : 0;
