@@ -80,6 +80,12 @@ static int set_err(int code, const char *fmt, const char *a = "",
                      cudaGetErrorString(_e));                                 \
   } while (0)
 
+// triclinic cells: sort grid over the Cartesian bounding box of the cell
+// (1) or over fractional coordinates (0)
+#ifndef RDFK_TRI_SORT_CART
+#define RDFK_TRI_SORT_CART 0
+#endif
+
 // ---------------------------------------------------------------------------
 // compile-time shape of the tile kernel
 // ---------------------------------------------------------------------------
@@ -113,6 +119,9 @@ struct FrameParams {
   float org[3];     // origin of prune space (per-frame minimum coordinate)
   float per[3];     // period in prune space (+inf: axis not periodic)
   float gscale[3];  // u * gscale in [0, 1): position inside the cell grid
+  // triclinic cells: the sort grid is laid over the CARTESIAN bounding box of
+  // the cell (origin, 1 / extent; sscale[0] == 0: use prune space instead)
+  float sorg[3], sscale[3];
   float wk[3];      // prune-space gap -> distance lower bound
   float rprune;     // group pair skipped iff bound > rprune
   float rshift;     // margin for the one-shift-per-group fast path
@@ -535,6 +544,7 @@ __global__ void params_kernel(int boxkind, const float *__restrict__ box,
       fp->L[k] = fp->inv[k] = fp->fl[k] = fp->finv[k] = 0.f;
       fp->tinv[k] = 0.f;
       fp->org[k] = (float)lo3[k];
+      fp->sorg[k] = fp->sscale[k] = 0.f;
       fp->per[k] = INFINITY;
       fp->wk[k] = 1.f;
       // no box / non-periodic axis: the grid spans the extents
@@ -620,6 +630,18 @@ __global__ void params_kernel(int boxkind, const float *__restrict__ box,
           fp->per[k] = 1.f;
           fp->gscale[k] = 1.f;
         }
+#if RDFK_TRI_SORT_CART
+        // Sort grid over the Cartesian bounding box of the cell: Hilbert
+        // neighbours in FRACTIONAL space are sheared blobs whose Cartesian
+        // boxes (the ones the quarter masks test) are mostly empty.
+        const double lo[3] = {fmin(0.0, bx) + fmin(0.0, cx), fmin(0.0, cy), 0.0};
+        const double hi[3] = {ax + fmax(0.0, bx) + fmax(0.0, cx),
+                              by + fmax(0.0, cy), cz};
+        for (int k = 0; k < 3; ++k) {
+          fp->sorg[k] = (float)lo[k];
+          fp->sscale[k] = (float)((1.0 - 1e-6) / (hi[k] - lo[k]));
+        }
+#endif
         scale = A[0] + A[1] + A[2] + fabs(ax) + fabs(bx) + fabs(by) +
                 fabs(cx) + fabs(cy) + fabs(cz);
         // fractional coordinates lose accuracy in very flat cells
@@ -836,14 +858,22 @@ __global__ __launch_bounds__(256) void key_kernel(
   const FrameParams &p = fparams[f];
   const float *g = staged + (size_t)f * 3 * np;
   float u0, u1, u2;
-  prune_coords<BOXKIND>(g[a], g[(size_t)np + a], g[2 * (size_t)np + a], p, u0,
-                        u1, u2);
+  float s0 = p.gscale[0], s1 = p.gscale[1], s2 = p.gscale[2];
+  if (BOXKIND == RDFK_BOX_TRI && p.sscale[0] > 0.f) {
+    u0 = __fsub_rn(g[a], p.sorg[0]);
+    u1 = __fsub_rn(g[(size_t)np + a], p.sorg[1]);
+    u2 = __fsub_rn(g[2 * (size_t)np + a], p.sorg[2]);
+    s0 = p.sscale[0]; s1 = p.sscale[1]; s2 = p.sscale[2];
+  } else {
+    prune_coords<BOXKIND>(g[a], g[(size_t)np + a], g[2 * (size_t)np + a], p,
+                          u0, u1, u2);
+  }
   const int m = 1 << bits;
   const float fm = (float)m;
   // NaN -> 0, out-of-grid -> clamped (pruning uses the real boxes anyway)
-  int c0 = __float2int_rd(__fmul_rn(__fmul_rn(u0, p.gscale[0]), fm));
-  int c1 = __float2int_rd(__fmul_rn(__fmul_rn(u1, p.gscale[1]), fm));
-  int c2 = __float2int_rd(__fmul_rn(__fmul_rn(u2, p.gscale[2]), fm));
+  int c0 = __float2int_rd(__fmul_rn(__fmul_rn(u0, s0), fm));
+  int c1 = __float2int_rd(__fmul_rn(__fmul_rn(u1, s1), fm));
+  int c2 = __float2int_rd(__fmul_rn(__fmul_rn(u2, s2), fm));
   c0 = max(0, min(m - 1, c0));
   c1 = max(0, min(m - 1, c1));
   c2 = max(0, min(m - 1, c2));
@@ -1037,6 +1067,23 @@ struct PairArgs {
 // so the rare band failure re-scans one group (resolve_entry).
 // ---------------------------------------------------------------------------
 constexpr int QS_MAX = 64;    // queue slots per lane (fail mask is 64 bits)
+// After every group a lane passes its queue column on by ROT lanes (odd, so
+// every column visits every lane).  Neighbouring lanes hold neighbouring atoms
+// and consecutive groups are neighbours too: with a step of 1 a column keeps
+// meeting lanes that are about as close to the current groups as the last one
+// was, and fills (or stays empty) accordingly.
+#ifndef RDFK_ROT
+#define RDFK_ROT 13
+#endif
+// logged / reserved parts a j-group is pushed in (1, 2 or 4).  Measured on
+// B200 (profiles/r2_notes.md): 2 parts -27 % (config 2), 4 parts -62 %: the
+// extra room checks / log entries / drain call sites cost far more than the
+// denser drain rows buy.
+#ifndef RDFK_GROUP_PARTS
+#define RDFK_GROUP_PARTS 1
+#endif
+constexpr int ROT = RDFK_ROT;
+static_assert(ROT % 2 == 1 && ROT > 0 && ROT < 32, "column step must be odd");
 // tunables of the triclinic instantiation (A/B builds: -DRDFK_...=n)
 #ifndef RDFK_TPB_TRI
 #define RDFK_TPB_TRI 256      // threads per CTA
@@ -1105,7 +1152,7 @@ struct Lay {
   static constexpr int OFF_IAT = OFF_CTX + SM_CTX;
   static constexpr int SM_WARP = OFF_IAT + SM_IAT;
   static constexpr int SM_FIXED = NW * SM_WARP;
-  static constexpr int NONPLAIN_UNROLL = TRI ? 1 : RI;
+  static constexpr int NONPLAIN_UNROLL = TRI ? 1 : RI / RDFK_GROUP_PARTS;
   static_assert(NTHR % 32 == 0 && NW >= 1 && NW <= 8, "1..8 warps per CTA");
   static_assert(QS >= PAIRS_PER_GROUP + GJ, "queue must absorb one group");
   static_assert(QS <= QS_MAX && QS % DWK == 0,
@@ -1220,12 +1267,13 @@ __device__ __noinline__ int resolve_entry(
     int swapped, float cut, const FrameParams *__restrict__ fp,
     const HistParams *__restrict__ hp) {
   // `col`: the queue column the entry sits in.  Columns rotate one lane per
-  // logged group, so the lane that pushed into it at log entry e was col + e.
+  // logged group, so the lane that pushed into it at log entry e was
+  // col + ROT * e.
   int e = 0;
   for (int t = 1; t < nlog; ++t)
     if ((int)mark[t * 32 + col] <= s) e = t;
   int rank = s - (int)mark[e * 32 + col];
-  const int lane = (col + e) & 31;
+  const int lane = (col + ROT * e) & 31;
   const int packed = glog[e];
   const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
             code = (packed >> 24) & 0x7f;
@@ -1551,7 +1599,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
       constexpr int DWL = decltype(width_tag)::value;
       __syncwarp();   // log and marks of the last group are visible to all lanes
       // my current column (the pointers rotate one lane per logged group)
-      const int col = (lane - nlog) & 31;
+      const int col = (lane - ROT * nlog) & 31;
       const int n = (int)((qaddr - qw_s) >> 7);
       const float *qcol = q + col;
       const int nmax = __reduce_max_sync(0xffffffffu, n);
@@ -1677,24 +1725,6 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
         __syncwarp();   // the fp64 loops above diverge per lane
         return;
       }
-      // room for this group (8 pairs per active quarter) in every queue
-      // column, and for one more entry in the log?
-      // (one vote for both conditions: its result is uniform for the compiler,
-      // so the branch around the drain needs no convergence barrier)
-      if (__any_sync(0xffffffffu,
-                     (nlog == LOGMAX) |
-                         (qaddr > qw_s + (QS - GJ * __popc(qmask)) * 128 + 127)))
-        drain();
-      RDFK_CHECK_THAT(a.header, nlog >= 0 && nlog < LOGMAX, CHK_LOG_OVERFLOW);
-      RDFK_CHECK_THAT(a.header,
-                      (int)((qaddr - qw_s) >> 7) + GJ * __popc(qmask) <= QS,
-                      CHK_QUEUE_OVERFLOW);
-      // (shared-window addresses: a generic store recomputes the window base)
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(glog_s + 4u * nlog), "r"(packed));
-      asm volatile("st.shared.u8 [%0], %1;" ::"r"(mark_s + 32u * nlog +
-                                                   ((lane - nlog) & 31)),
-                   "r"((qaddr - qw_s) >> 7));
-      ++nlog;
       if (__any_sync(0xffffffffu, code != cur_code)) {
         float sx = 0.f, sy = 0.f, sz = 0.f;
         if (BOXKIND != RDFK_BOX_NONE && (code & CODE_PLAIN)) {
@@ -1714,77 +1744,116 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
         }
         cur_code = code;
       }
-      if ((BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN)) {
-        // plain: 3 FADD2 + FMUL2 + 2 FFMA2 and 2 x 3 queue instructions per
-        // two pairs; j-atom pairs come straight out of the LDS.128 registers,
-        // the i-atom is a broadcast scalar operand.  Quarters that cannot
-        // reach the group are skipped (warp-uniform).
-        // The group is read from shared memory once (6 LDS.128), not once per
-        // quarter: the shared-memory pipe is the kernel's co-bottleneck
-        // (65 % of peak wavefronts, profiles/r1_notes.md).
+      // The group is read from shared memory once (6 LDS.128), not once per
+      // quarter: the shared-memory pipe is the kernel's co-bottleneck
+      // (65 % of peak wavefronts, profiles/r1_notes.md).  j-atom pairs come
+      // straight out of the LDS.128 registers.
+      uint64_t xj2[4], yj2[4], zj2[4];
+      auto load_group = [&]() {
         const ulonglong2 X0 = *reinterpret_cast<const ulonglong2 *>(js);
         const ulonglong2 X1 = *reinterpret_cast<const ulonglong2 *>(js + 4);
         const ulonglong2 Y0 = *reinterpret_cast<const ulonglong2 *>(js + GJ);
         const ulonglong2 Y1 = *reinterpret_cast<const ulonglong2 *>(js + GJ + 4);
         const ulonglong2 Z0 = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ);
         const ulonglong2 Z1 = *reinterpret_cast<const ulonglong2 *>(js + 2 * GJ + 4);
-        const uint64_t xj2[4] = {X0.x, X0.y, X1.x, X1.y};
-        const uint64_t yj2[4] = {Y0.x, Y0.y, Y1.x, Y1.y};
-        const uint64_t zj2[4] = {Z0.x, Z0.y, Z1.x, Z1.y};
+        xj2[0] = X0.x; xj2[1] = X0.y; xj2[2] = X1.x; xj2[3] = X1.y;
+        yj2[0] = Y0.x; yj2[1] = Y0.y; yj2[2] = Y1.x; yj2[3] = Y1.y;
+        zj2[0] = Z0.x; zj2[1] = Z0.y; zj2[2] = Z1.x; zj2[3] = Z1.y;
+      };
+      load_group();
+      const bool plain = (BOXKIND == RDFK_BOX_NONE) || (code & CODE_PLAIN);
+      // A group is pushed in PARTS of RI / PARTS quarters, each with its own
+      // room check, log entry and column hand-over (PARTS = 1: the group as a
+      // whole).  The room check has to reserve the worst case (every pair a
+      // hit); smaller parts would let the columns fill further before a drain
+      // is forced (config 4, hit rate 12 %: only 29 % of the drained slots
+      // hold an entry) -- see RDFK_GROUP_PARTS for why that did not pay.
+      constexpr int PARTS = RDFK_GROUP_PARTS, QPP = RI / PARTS;
+#pragma unroll(L::IAT_SMEM ? 1 : PARTS)
+      for (int part = 0; part < PARTS; ++part) {
+        const int qm = PARTS == 1 ? qmask
+                                  : (qmask & (((1 << QPP) - 1) << (QPP * part)));
+        if (PARTS > 1 && qm == 0) continue;   // (warp-uniform: from the word)
+        // room for this part (8 pairs per active quarter) in every queue
+        // column, and for one more entry in the log?
+        // (one vote for both conditions: its result is uniform for the
+        // compiler, so the branch around the drain needs no convergence
+        // barrier)
+        if (__any_sync(0xffffffffu,
+                       (nlog == LOGMAX) |
+                           (qaddr > qw_s + (QS - GJ * __popc(qm)) * 128 + 127))) {
+          drain();
+          load_group();   // (re-read rather than kept alive across the drain)
+        }
+        RDFK_CHECK_THAT(a.header, nlog >= 0 && nlog < LOGMAX, CHK_LOG_OVERFLOW);
+        RDFK_CHECK_THAT(a.header,
+                        (int)((qaddr - qw_s) >> 7) + GJ * __popc(qm) <= QS,
+                        CHK_QUEUE_OVERFLOW);
+        // the log entry names the quarters of THIS part
+        const int word = (packed & ~(15 << G_BITS)) | (qm << G_BITS);
+        // (shared-window addresses: a generic store recomputes the window base)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(glog_s + 4u * nlog), "r"(word));
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(mark_s + 32u * nlog +
+                                                     ((lane - ROT * nlog) & 31)),
+                     "r"((qaddr - qw_s) >> 7));
+        ++nlog;
+        if (plain) {
+          // plain: 3 FADD2 + FMUL2 + 2 FFMA2 and 2 x 3 queue instructions per
+          // two pairs; the i-atom is a broadcast scalar operand.  Quarters
+          // that cannot reach the group are skipped (warp-uniform).
 #pragma unroll
-        for (int r = 0; r < RI; ++r) {
-          if (!((qmask >> r) & 1)) continue;
-          const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
-          const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
-          const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
-          const uint64_t nx2 = pk2(nxr, nxr), ny2 = pk2(nyr, nyr),
-                         nz2 = pk2(nzr, nzr);
+          for (int rr = 0; rr < QPP; ++rr) {
+            const int r = part * QPP + rr;
+            if (!((qm >> r) & 1)) continue;
+            const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
+            const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
+            const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
+            const uint64_t nx2 = pk2(nxr, nxr), ny2 = pk2(nyr, nyr),
+                           nz2 = pk2(nzr, nzr);
 #pragma unroll
-          for (int up = 0; up < GJ / 2; ++up) {
-            const uint64_t dx = add2(xj2[up], nx2), dy = add2(yj2[up], ny2),
-                           dz = add2(zj2[up], nz2);
-            const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-            float ra, rb;
-            unpk2(t, ra, rb);
-            q_push(qaddr, ra, cut);
-            q_push(qaddr, rb, cut);
+            for (int up = 0; up < GJ / 2; ++up) {
+              const uint64_t dx = add2(xj2[up], nx2), dy = add2(yj2[up], ny2),
+                             dz = add2(zj2[up], nz2);
+              const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+              float ra, rb;
+              unpk2(t, ra, rb);
+              q_push(qaddr, ra, cut);
+              q_push(qaddr, rb, cut);
+            }
+          }
+        } else {
+          // per-pair minimum image (ortho rint / triclinic brick), same order
+          // (triclinic: one copy of the quarter body -- 8 brick reductions;
+          // this path is rare there and the instantiation is instruction-cache
+          // bound)
+          const FastBox fb = load_fastbox(fp);
+#pragma unroll(L::NONPLAIN_UNROLL)
+          for (int rr = 0; rr < QPP; ++rr) {
+            const int r = part * QPP + rr;
+            if (!((qm >> r) & 1)) continue;
+            const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
+            const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
+            const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
+#pragma unroll
+            for (int up = 0; up < GJ / 2; ++up) {
+              float xa, xb, ya, yb, za, zb;
+              unpk2(xj2[up], xa, xb);
+              unpk2(yj2[up], ya, yb);
+              unpk2(zj2[up], za, zb);
+              q_push(qaddr,
+                     pair_r2<BOXKIND, false>(xa, ya, za, nxr, nyr, nzr, fb), cut);
+              q_push(qaddr,
+                     pair_r2<BOXKIND, false>(xb, yb, zb, nxr, nyr, nzr, fb), cut);
+            }
           }
         }
-      } else {
-        // per-pair minimum image (ortho rint / triclinic brick), same order
-        const FastBox fb = load_fastbox(fp);
-        const float4 Xa = *reinterpret_cast<const float4 *>(js);
-        const float4 Xb = *reinterpret_cast<const float4 *>(js + 4);
-        const float4 Ya = *reinterpret_cast<const float4 *>(js + GJ);
-        const float4 Yb = *reinterpret_cast<const float4 *>(js + GJ + 4);
-        const float4 Za = *reinterpret_cast<const float4 *>(js + 2 * GJ);
-        const float4 Zb = *reinterpret_cast<const float4 *>(js + 2 * GJ + 4);
-        const float xj8[GJ] = {Xa.x, Xa.y, Xa.z, Xa.w, Xb.x, Xb.y, Xb.z, Xb.w};
-        const float yj8[GJ] = {Ya.x, Ya.y, Ya.z, Ya.w, Yb.x, Yb.y, Yb.z, Yb.w};
-        const float zj8[GJ] = {Za.x, Za.y, Za.z, Za.w, Zb.x, Zb.y, Zb.z, Zb.w};
-        // (triclinic: one copy of the quarter body -- 8 brick reductions --
-        // instead of four; this path is rare there and the instantiation is
-        // instruction-cache bound)
-#pragma unroll(L::NONPLAIN_UNROLL)
-        for (int r = 0; r < RI; ++r) {
-          if (!((qmask >> r) & 1)) continue;
-          const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
-          const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
-          const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
-#pragma unroll
-          for (int u = 0; u < GJ; ++u)
-            q_push(qaddr,
-                   pair_r2<BOXKIND, false>(xj8[u], yj8[u], zj8[u], nxr, nyr,
-                                           nzr, fb),
-                   cut);
-        }
+        RDFK_CHECK_THAT(a.header, (int)((qaddr - qw_s) >> 7) <= QS,
+                        CHK_QUEUE_OVERFLOW);
+        // hand my queue column on: every column collects the hits of many
+        // different i-atoms, so the columns fill evenly and the rows the
+        // drain walks are denser
+        qaddr = __shfl_sync(0xffffffffu, qaddr, (lane + 32 - ROT) & 31);
       }
-      RDFK_CHECK_THAT(a.header, (int)((qaddr - qw_s) >> 7) <= QS,
-                      CHK_QUEUE_OVERFLOW);
-      // hand my queue column to the next lane: every column collects the hits
-      // of many different i-atoms, so the columns fill evenly and the rows the
-      // drain walks are denser
-      qaddr = __shfl_sync(0xffffffffu, qaddr, (lane + 31) & 31);
     };
 
     // Level 1: 32 j-clusters per round against my cluster box.  Level 2: the
