@@ -1665,16 +1665,7 @@ def _run_hbonds_part(device, traj, natoms, segs, n_blocks, n_frames, spec):
                     kinds, box9, _ = _box_rows(dims, B)
                     lo_f = pos0 + done
                     out["io"][lo_f:lo_f + B] = t_io / B
-                    # allocated and filled on the batch's compute stream: the
-                    # host runs batches ahead of the device, and a block freed
-                    # on another stream could be handed out again (and
-                    # overwritten) while this batch's kernels still wait
-                    with (torch.cuda.stream(st.compute_stream) if cuda
-                          else _nullctx()):
-                        box_d = torch.as_tensor(box9, device=device)
-                    if cuda:
-                        st.compute_stream.wait_stream(
-                            torch.cuda.current_stream(device))
+                    box_d = _dev_const(st, box9, np.float32)
                     out["first_launch"][b] = min(out["first_launch"][b],
                                                  time.time())
                     tm = _Timer(st)

@@ -11,7 +11,7 @@ import numpy as np
 from pmda_b200 import synthetic
 from oracle import c_oracle
 
-T = c_oracle.max_threads()
+T = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
 
 
 def sample(pos, i1, i2, dims, nbins, rng, rows, threads, cells):
