@@ -53,7 +53,7 @@ static HbLayout hb_layout(int F, int n_dh, int n_acc) {
   w.fparams = off;
   off = align_up(off + sizeof(FrameParams) * (size_t)F, 256);
   w.tables = off;
-  off = align_up(off + sizeof(float2) * 2 * 2, 256);
+  off = align_up(off + sizeof(float2) * 2 * 3, 256);   // [2][nbins + 2], nbins = 1
   w.edges = off;
   off = align_up(off + sizeof(double) * 2, 256);
   w.gd = off;
@@ -205,7 +205,7 @@ __global__ __launch_bounds__(256) void hb_kernel(const HbArgs a) {
   // pads of the staged arrays are NaN: never a candidate
   const float xd = valid ? gd[k] : nan, yd = valid ? gd[a.npd + k] : nan,
               zd = valid ? gd[2 * (size_t)a.npd + k] : nan;
-  const float nxd = -xd, nyd = -yd, nzd = -zd;
+  const float nxd = xd, nyd = yd, nzd = zd;   // (pair_r2 subtracts)
   float xh = 0.f, yh = 0.f, zh = 0.f;
   if (a.has_h && valid) {
     const float *gh = a.gh + (size_t)f * 3 * a.npd;
@@ -507,7 +507,7 @@ __global__ __launch_bounds__(256) void hb_cells_kernel(const HbArgs a) {
   const float nan = __int_as_float(0x7fc00000);
   const float xd = valid ? gd[k] : nan, yd = valid ? gd[a.npd + k] : nan,
               zd = valid ? gd[2 * (size_t)a.npd + k] : nan;
-  const float nxd = -xd, nyd = -yd, nzd = -zd;
+  const float nxd = xd, nyd = yd, nzd = zd;   // (pair_r2 subtracts)
   float xh = 0.f, yh = 0.f, zh = 0.f;
   if (a.has_h && valid) {
     const float *gh = a.gh + (size_t)f * 3 * a.npd;

@@ -201,7 +201,7 @@ static WsLayout ws_layout(int F, int n1, int n2, int nbins, int same_group) {
   w.fparams = off;
   off = align_up(off + sizeof(FrameParams) * (size_t)F, 256);
   w.tables = off;
-  off = align_up(off + sizeof(float2) * 2 * ((size_t)nbins + 1), 256);
+  off = align_up(off + sizeof(float2) * 2 * ((size_t)nbins + 2), 256);
   w.g1 = off;
   off = align_up(off + sizeof(float) * 3 * (size_t)w.np1 * (size_t)F, 256);
   w.g2 = same_group ? w.g1 : off;
@@ -679,6 +679,9 @@ __global__ void params_kernel(int boxkind, const float *__restrict__ box,
     }
     const double delta = sqrt(dk[0] * dk[0] + dk[1] * dk[1] + dk[2] * dk[2]);
     if (!(delta < 1e30)) slow = true;
+    // the pair kernel's candidate bin of an r2 < r2_cut must stay <= nbins
+    // (and decision bands this wide would decide next to nothing anyway)
+    if (!(delta * 1.01 < 0.25 * (hp.r1 - hp.r0) / (double)hp.nbins)) slow = true;
     if (slow) shift_ok = false;
     // tight table: no shift, n = 0 on every axis.  fp32 dx equals the
     // reference's float difference; the reference then multiplies by
@@ -753,11 +756,16 @@ __global__ __launch_bounds__(256) void tables_kernel(
       const float r = nextafterf(__double2float_rd(v), 0.f);
       return r > 0.f ? r : 0.f;
     };
-    // entry k + 1 decides bin k; entry 0 is "certainly below r0: drop"
-    float2 *tab = tables + (size_t)w * (nbins + 1);
-    for (int k = threadIdx.x; k <= nbins; k += blockDim.x) {
+    // entry k + 1 decides bin k; entry 0 is "certainly below r0: drop";
+    // entry nbins + 1 never decides anything (candidate "bin nbins" of an r2
+    // in the error band above r1: fp64 path)
+    float2 *tab = tables + (size_t)w * (nbins + 2);
+    for (int k = threadIdx.x; k <= nbins + 1; k += blockDim.x) {
       float lo, hi;
-      if (k == 0) {
+      if (k == nbins + 1) {
+        lo = INFINITY;
+        hi = INFINITY;
+      } else if (k == 0) {
         lo = -INFINITY;
         hi = hp.edges[0] > 0.0 ? t_lo(hp.edges[0]) : 0.f;
       } else {
@@ -1047,9 +1055,10 @@ struct PairArgs {
   int nslice;         // every later (frame, i-cluster) is cut into `nslice`
                       // work items along its j-clusters
   const FrameParams *fparams;
-  const float2 *tables;   // [F][2][nbins + 1]
+  const float2 *tables;   // [2][nbins + 2]
   HistParams hp;
   int hist_copies;    // warp-private shared copies (0 = global atomics)
+  uint32_t kbias;     // 0x4B400000 = bits of 1.5 * 2^23 (see drain_w)
   unsigned long long *hist;
   WsHeader *header;
 };
@@ -1081,6 +1090,12 @@ constexpr int QS_MAX = 64;    // queue slots per lane (fail mask is 64 bits)
 // denser drain rows buy.
 #ifndef RDFK_GROUP_PARTS
 #define RDFK_GROUP_PARTS 1
+#endif
+#ifndef RDFK_R0FAST_TRI
+#define RDFK_R0FAST_TRI 0
+#endif
+#ifndef RDFK_PK_PER_USE
+#define RDFK_PK_PER_USE 1
 #endif
 constexpr int ROT = RDFK_ROT;
 static_assert(ROT % 2 == 1 && ROT > 0 && ROT < 32, "column step must be odd");
@@ -1114,6 +1129,10 @@ constexpr int DW = 16;        // queue entries per lane in flight in the drain
 #define RDFK_DW_TRI 8
 #endif
 constexpr int DW_TRI = RDFK_DW_TRI;
+// slots per batch of the R0ZERO drain (look-ups in flight per lane)
+#ifndef RDFK_DRAIN_BATCH
+#define RDFK_DRAIN_BATCH 8
+#endif
 
 constexpr int SM_ST = NSTAGE * 3 * GJ * 4;     // staged j-groups
 constexpr int SM_CODE = NSTAGE * 4;            // their (group, code, quarter mask)
@@ -1224,12 +1243,22 @@ __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
+__device__ __forceinline__ uint64_t pk2v(float lo, float hi) {
+  uint64_t r;
+  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
 __device__ __forceinline__ void unpk2(uint64_t v, float &lo, float &hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
@@ -1243,13 +1272,13 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   return d;
 }
 
-// r2 of one pair; (nxi, nyi, nzi) = minus the (shifted) i coordinates.
+// r2 of one pair; (pxi, pyi, pzi) = the (shifted) i coordinates.
 // PLAIN: the lattice shift is already in the i coordinates.
 template <int BOXKIND, bool PLAIN>
-__device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float nxi,
-                                         float nyi, float nzi, const FastBox &fb) {
-  const float dx = __fadd_rn(xj, nxi), dy = __fadd_rn(yj, nyi),
-              dz = __fadd_rn(zj, nzi);
+__device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float pxi,
+                                         float pyi, float pzi, const FastBox &fb) {
+  const float dx = __fsub_rn(xj, pxi), dy = __fsub_rn(yj, pyi),
+              dz = __fsub_rn(zj, pzi);
   if (PLAIN || BOXKIND == RDFK_BOX_NONE)
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
   return r2_fast<BOXKIND>(dx, dy, dz, fb);
@@ -1286,8 +1315,8 @@ __device__ __noinline__ int resolve_entry(
     if (!((qmask >> r) & 1)) continue;
     const float xr = gi_cl[r * 32 + lane], yr = gi_cl[np_i + r * 32 + lane],
                 zr = gi_cl[2 * np_i + r * 32 + lane];
-    const float nxi = -__fadd_rn(xr, sx), nyi = -__fadd_rn(yr, sy),
-                nzi = -__fadd_rn(zr, sz);
+    const float nxi = __fadd_rn(xr, sx), nyi = __fadd_rn(yr, sy),
+                nzi = __fadd_rn(zr, sz);
     for (int u = 0; u < GJ; ++u) {
       const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
       const float r2 = plain ? pair_r2<BOXKIND, true>(xj, yj, zj, nxi, nyi, nzi, fb)
@@ -1303,10 +1332,17 @@ __device__ __noinline__ int resolve_entry(
   return -2;  // unreachable: the entry was produced by one of these pairs
 }
 
-template <int BOXKIND, bool GLOBAL_HIST>
+// R0ZERO: the histogram range starts at 0 (the default, and every BASELINE
+// configuration): the candidate bin of a queue entry is floor(sqrt(r2) / dr),
+// ONE round-down FFMA onto the 1.5 * 2^23 magic number, and it needs no clamp:
+// it cannot be negative, and r2 < r2_cut keeps it <= nbins (params_kernel sends
+// frames whose error bound is not far below the bin width to the fp64 path),
+// for which the tables hold an entry that never decides.
+template <int BOXKIND, bool GLOBAL_HIST, bool R0ZERO>
 __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
     const PairArgs a) {
   static_assert(RI == 4 && GJ == 8 && GPC == 16, "written for 4 x 8, 16 groups");
+  static_assert(!(GLOBAL_HIST && R0ZERO), "the fast drain reads shared tables");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ HistParams s_hp;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1337,6 +1373,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
   // the two decision tables of the call: shared memory (after the histogram
   // copies) unless the histogram itself did not fit
   const int nb1 = nbins + 1;
+  const int nbt = nbins + 2;   // entries per decision table
   const size_t hist_bytes = (((size_t)copies * nb1 * 4) + 15) & ~(size_t)15;
   float2 *tab_s = reinterpret_cast<float2 *>(smem_raw + SM_FIXED + hist_bytes);
   const uint32_t tab_s32 = smem_u32(tab_s);
@@ -1357,7 +1394,14 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
 
   for (int b = tid; b < copies * hstride; b += L::NTHR) hist_s[b] = 0u;
   if (!GLOBAL_HIST)
-    for (int b = tid; b < 2 * nb1; b += L::NTHR) tab_s[b] = a.tables[b];
+    for (int b = tid; b < 2 * nbt; b += L::NTHR) tab_s[b] = a.tables[b];
+  if (R0ZERO) {
+    // The fast drain computes a table address from every slot of a drained
+    // row, dead ones included: they must hold an r2 that was pushed once (or
+    // zero), never the garbage shared memory starts with.
+    for (int b = lane; b < QS * 32; b += 32) q[b] = 0.f;
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(dummy_s), "r"(0u) : "memory");
+  }
   if (tid == 0) s_hp = a.hp;
   __syncthreads();
 
@@ -1568,7 +1612,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
       return m;
     };
 
-    // minus my (shifted) i-atoms
+    // my (shifted) i-atoms
     int cur_code = -1;
     float nxs[RI], nys[RI], nzs[RI];
     int nlog = 0;
@@ -1604,9 +1648,71 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
       const float *qcol = q + col;
       const int nmax = __reduce_max_sync(0xffffffffu, n);
       const float inv_dr = fp->inv_dr, koffm = fp->koffm;
-      const unsigned int toff = cls ? (unsigned int)nb1 + 1u : 1u;
+      const unsigned int toff = cls ? (unsigned int)nbt + 1u : 1u;
+      // R0ZERO: addresses straight from the bits of kf = 1.5 * 2^23 + k
+      // (0x4B400000 + k); the constant part wraps modulo 2^32
+      // (opaque to the compiler: it would split the constant off again and
+      // spend a second instruction per slot on adding it back)
+      // (a.kbias = 0x4B400000 is a kernel argument so that ptxas cannot split
+      // the constant off again and spend a second instruction per slot on
+      // adding it back)
+      const uint32_t tab_k = tab_s32 + 8u * toff - (a.kbias << 3);
+      const uint32_t hist_k = wh_s - (a.kbias << 2);
+      // slot -> live and certainly in its candidate bin (R0ZERO; used by the
+      // drain loop and, bit for bit the same, by the rare re-scan for failed
+      // entries)
+      auto slot_ok = [&](float r2, bool live, uint32_t &kb) -> bool {
+        kb = __float_as_uint(__fmaf_rd(sqrt_approx(r2), inv_dr, MAGIC));
+        float2 t;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(t.x), "=f"(t.y)
+                     : "r"(tab_k + (kb << 3)));
+        return live & (r2 >= t.x) & (r2 < t.y);
+      };
       unsigned long long failmask = 0ull;   // bit s: entry s needs the fp64 path
-      for (int s = 0; s < nmax; s += DWL) {
+      // R0ZERO: batches of BW slots -- all their table look-ups are issued
+      // before the first atomic (the compiler keeps shared loads behind earlier
+      // shared atomics: interleaved, every slot waited for its own look-up),
+      // and no per-slot bookkeeping: every slot that is not certain (dead ones
+      // included) adds `weight` to my dummy word, which is compared with the
+      // number of dead slots after the loop
+      constexpr int BW = DWL < RDFK_DRAIN_BATCH ? DWL : RDFK_DRAIN_BATCH;
+      if (R0ZERO) {
+        for (int s = 0; s < nmax; s += BW) {
+          float v[BW];
+          uint32_t kb[BW];
+          float2 t[BW];
+#pragma unroll
+          for (int u = 0; u < BW; ++u) v[u] = qcol[(s + u) * 32];
+#pragma unroll
+          for (int u = 0; u < BW; ++u) {
+            kb[u] = __float_as_uint(__fmaf_rd(sqrt_approx(v[u]), inv_dr, MAGIC));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(t[u].x), "=f"(t[u].y)
+                         : "r"(tab_k + (kb[u] << 3)));
+          }
+          const int rem = n - s;   // entries s .. s + rem - 1 are live
+#pragma unroll
+          for (int u = 0; u < BW; ++u) {
+            // (one predicate chain and one select: written as `a & b & c ? x
+            // : y` the compiler emits three selects)
+            uint32_t ha;
+            asm("{\n"
+                ".reg .pred p;\n"
+                "setp.ge.f32 p, %1, %2;\n"
+                "setp.gt.and.s32 p, %4, %5, p;\n"
+                "setp.lt.and.f32 p, %1, %3, p;\n"
+                "selp.u32 %0, %6, %7, p;\n"
+                "}\n"
+                : "=r"(ha)
+                : "f"(v[u]), "f"(t[u].x), "f"(t[u].y), "r"(rem), "r"(u),
+                  "r"(hist_k + (kb[u] << 2)), "r"(dummy_s));
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ha), "r"(weight)
+                         : "memory");
+          }
+        }
+      }
+      for (int s = 0; !R0ZERO && s < nmax; s += DWL) {
         float v[DWL];
 #pragma unroll
         for (int u = 0; u < DWL; ++u) v[u] = qcol[(s + u) * 32];
@@ -1650,7 +1756,41 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
             rem >= DWL ? (unsigned int)((1ull << DWL) - 1ull)
                       : ((1u << (rem > 0 ? rem : 0)) - 1u);
         const unsigned int fail = livemask & ~okmask;
-        failmask |= (unsigned long long)fail << s;
+        if (!R0ZERO) failmask |= (unsigned long long)fail << s;
+      }
+      if (R0ZERO) {
+        unsigned int dsum;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dsum) : "r"(dummy_s) : "memory");
+        const int rows = (nmax + BW - 1) / BW * BW;   // slots I walked
+        const bool failed = dsum != weight * (unsigned int)(rows - n);
+        if (__any_sync(0xffffffffu, failed)) {
+          // rare: find my failed entries again (same arithmetic, same bits)
+          if (failed) {
+            // (four entries in flight: one at a time, the look-up latencies of
+            // this loop were 8 % of the kernel's stall samples)
+#pragma unroll 1
+            for (int s = 0; s < n; s += 4) {
+              float v[4];
+              bool ok[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)   // (never past my n entries)
+                v[u] = s + u < n ? qcol[(s + u) * 32] : 0.f;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint32_t kb;
+                ok[u] = slot_ok(v[u], true, kb);
+              }
+              unsigned int bad = 0u;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) bad |= ok[u] ? 0u : (1u << u);
+              failmask |= (unsigned long long)bad << s;
+            }
+            // (slots past n were given r2 = 0)
+            failmask &= n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+          }
+          __syncwarp();
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(dummy_s), "r"(0u) : "memory");
       }
       // the rare band failures, after the pipelined loop
       if (__any_sync(0xffffffffu, failmask != 0ull)) {
@@ -1733,9 +1873,11 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
         }
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-          const float vx = -__fadd_rn(gi_cl[r * 32 + lane], sx);
-          const float vy = -__fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
-          const float vz = -__fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
+          // (kept positive and subtracted: with the negated copies ptxas held
+          // both signs in registers and spent two moves per packed operand)
+          const float vx = __fadd_rn(gi_cl[r * 32 + lane], sx);
+          const float vy = __fadd_rn(gi_cl[np_i + r * 32 + lane], sy);
+          const float vz = __fadd_rn(gi_cl[2 * np_i + r * 32 + lane], sz);
           if (L::IAT_SMEM) {
             iat[r * 32] = vx; iat[CI + r * 32] = vy; iat[2 * CI + r * 32] = vz;
           } else {
@@ -1808,12 +1950,19 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
             const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
             const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
             const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
-            const uint64_t nx2 = pk2(nxr, nxr), ny2 = pk2(nyr, nyr),
-                           nz2 = pk2(nzr, nzr);
 #pragma unroll
             for (int up = 0; up < GJ / 2; ++up) {
-              const uint64_t dx = add2(xj2[up], nx2), dy = add2(yj2[up], ny2),
-                             dz = add2(zj2[up], nz2);
+              // (a pack per use: ptxas folds a single-use {a, a} into the
+              // FADD2 as a broadcast operand, a shared one costs two moves)
+#if RDFK_PK_PER_USE
+              const uint64_t nx2 = pk2v(nxr, nxr), ny2 = pk2v(nyr, nyr),
+                             nz2 = pk2v(nzr, nzr);
+#else
+              const uint64_t nx2 = pk2(nxr, nxr), ny2 = pk2(nyr, nyr),
+                             nz2 = pk2(nzr, nzr);
+#endif
+              const uint64_t dx = sub2(xj2[up], nx2), dy = sub2(yj2[up], ny2),
+                             dz = sub2(zj2[up], nz2);
               const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
               float ra, rb;
               unpk2(t, ra, rb);
@@ -2373,7 +2522,7 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   // warp-private histogram copies: one per warp if two CTAs still fit on
   // an SM, otherwise as many as one CTA can hold, otherwise global atomics
   const size_t per_copy = ((size_t)hp.nbins + 1) * sizeof(unsigned int);
-  const size_t tab_bytes = 2 * ((size_t)hp.nbins + 1) * sizeof(float2) + 16;
+  const size_t tab_bytes = 2 * ((size_t)hp.nbins + 2) * sizeof(float2) + 16;
   constexpr int SM_FIXED = Lay<BOXKIND>::SM_FIXED;
   // (two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA, 128 B
   // of static shared memory in the kernel)
@@ -2386,10 +2535,18 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
     copies = (int)((one_cta - tab_bytes) / per_copy);
   if (copies > NW) copies = NW;
   a.hist_copies = copies;
+  a.kbias = 0x4B400000u;
   const size_t smem =
       (size_t)SM_FIXED + (copies ? (size_t)copies * per_copy + tab_bytes : 0);
-  void (*kern)(const PairArgs) = copies ? pair_prune_kernel<BOXKIND, false>
-                                        : pair_prune_kernel<BOXKIND, true>;
+  // (debug flag bit 4: the general drain although the range starts at 0)
+  // (the triclinic instantiation is instruction-cache bound: with the fast
+  // drain and its re-scan it ran 1 142 instead of 1 319 frames/s at config 4)
+  const bool r0zero = copies && hp.r0 == 0.0 && !(debug_flags & 16) &&
+                      (BOXKIND != RDFK_BOX_TRI || RDFK_R0FAST_TRI);
+  void (*kern)(const PairArgs) = copies ? pair_prune_kernel<BOXKIND, false, false>
+                                        : pair_prune_kernel<BOXKIND, true, false>;
+  if constexpr (BOXKIND != RDFK_BOX_TRI || RDFK_R0FAST_TRI)
+    if (r0zero) kern = pair_prune_kernel<BOXKIND, false, true>;
   // the attribute / occupancy queries cost more than a launch: remembered per
   // (device, instantiation, shared-memory size); thread_local, no locking
   struct OccCache { int dev; void *fn; size_t smem; int occ; };

@@ -1,8 +1,9 @@
 """GPU parity for the sorted / pruned pair kernel: everything the spatial sort,
 the box tests and the one-shift-per-group fast path could get wrong must still
 give the oracle's integers.  rdfk_set_debug_flags (bit 0: no pruning, bit 1: no shifted
-variant, bit 2: no Euclidean refinement of the triclinic box test) is read by
-librdfk on every call; results must not depend on it."""
+variant, bit 2: no Euclidean refinement of the triclinic box test, bit 4: the
+general drain although the range starts at 0) is read by librdfk on every call;
+results must not depend on it."""
 import os
 
 import numpy as np
@@ -29,7 +30,7 @@ def _gpu(u, g1, g2, nbins=75, rng=(0.0, 15.0), excl=None, debug=None):
 
 def _check_all_modes(u, g1, g2, nbins=75, rng=(0.0, 15.0), excl=None):
     want, _, _ = oracle_interrdf(u, g1, g2, nbins, rng, excl)
-    for debug in (None, 1, 2, 3, 4, 6):
+    for debug in (None, 1, 2, 3, 4, 6, 16, 19):
         got = _gpu(u, g1, g2, nbins, rng, excl, debug)
         np.testing.assert_array_equal(got, want, err_msg="debug flags %r" % debug)
     return want

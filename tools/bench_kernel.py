@@ -10,6 +10,9 @@ from pmda_b200.rdf import InterRDF
 FRAMES = {1: 100, 2: 128, 4: 48, 5: 24}
 cfgs = [int(a) for a in sys.argv[1:]] or [2, 4]
 engine.Config.cache_bytes = 64 << 30
+if os.environ.get("RDFK_FLAGS"):   # rdfk_set_debug_flags (A/B of code paths)
+    from pmda_b200 import _cabi
+    _cabi.set_debug_flags(int(os.environ["RDFK_FLAGS"], 0))
 out = []
 for cfg in cfgs:
     u, kw = synthetic.CONFIGS[cfg](n_frames=FRAMES[cfg])
@@ -24,4 +27,5 @@ for cfg in cfgs:
         kern = min(kern, float(r.timing.compute.sum()))
     out.append("cfg%d resident %.0f kernel %.0f" % (cfg, FRAMES[cfg] / best, FRAMES[cfg] / kern))
     del u, kw, r
-print(os.environ.get("RDFK_LIB", "default"), " | ".join(out), flush=True)
+print(os.environ.get("RDFK_LIB", "default"), os.environ.get("RDFK_FLAGS", ""),
+      " | ".join(out), flush=True)
