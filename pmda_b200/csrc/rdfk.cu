@@ -1284,25 +1284,31 @@ __device__ __forceinline__ float pair_r2(float xj, float yj, float zj, float pxi
   return r2_fast<BOXKIND>(dx, dy, dz, fb);
 }
 
-// Rare path: entry `s` of queue column `col` failed the band test.  Find the
-// group it came from (marks), re-scan that group in the hot loop's order with
-// the hot loop's arithmetic, and bin the pair with the reference arithmetic.
-// Hot-loop order: the quarters of the mask (i-atom r = 0..RI-1), inside the
-// eight j-atoms in order.
+// Rare path: entry `s` of queue column `col` failed the band test.  The WHOLE
+// WARP resolves it (one lane doing it alone kept the other 31 waiting through
+// ~600 dependent instructions; that was 10 % of the kernel's stall samples):
+// lane t looks at the mark of log entry t to find the group the entry came
+// from, then lane 8 r + u re-evaluates pair (i-atom r of the pushing lane, j-atom
+// u of the group) with the hot loop's arithmetic -- the hot loop pushes in
+// exactly this order (quarters of the mask, inside them the eight j-atoms) --
+// and the lane holding the entry's hit bins it with the reference arithmetic.
+// Warp-uniform arguments; returns the bin in every lane (-1: not binned, -2:
+// unreachable, the entry was produced by one of these pairs).
 template <int BOXKIND>
 __device__ __noinline__ int resolve_entry(
     int s, int col, const unsigned char *mark, const int *glog, int nlog,
     const float *gi_cl, size_t np_i, const float *gj_f, size_t np_j,
     int swapped, float cut, const FrameParams *__restrict__ fp,
     const HistParams *__restrict__ hp) {
-  // `col`: the queue column the entry sits in.  Columns rotate one lane per
+  const int lane = threadIdx.x & 31;
+  // `col`: the queue column the entry sits in.  Columns move on ROT lanes per
   // logged group, so the lane that pushed into it at log entry e was
   // col + ROT * e.
-  int e = 0;
-  for (int t = 1; t < nlog; ++t)
-    if ((int)mark[t * 32 + col] <= s) e = t;
-  int rank = s - (int)mark[e * 32 + col];
-  const int lane = (col + ROT * e) & 31;
+  const unsigned int em = __ballot_sync(
+      0xffffffffu, lane < nlog && (lane == 0 || (int)mark[lane * 32 + col] <= s));
+  const int e = 31 - __clz((int)em);
+  const int rank = s - (int)mark[e * 32 + col];
+  const int src = (col + ROT * e) & 31;
   const int packed = glog[e];
   const int g = packed & ((1 << G_BITS) - 1), qmask = (packed >> G_BITS) & 15,
             code = (packed >> 24) & 0x7f;
@@ -1310,26 +1316,24 @@ __device__ __noinline__ int resolve_entry(
   const bool plain = (code & CODE_PLAIN) != 0;
   float sx = 0.f, sy = 0.f, sz = 0.f;
   if (plain && BOXKIND != RDFK_BOX_NONE) decode_shift<BOXKIND>(code, fb, sx, sy, sz);
+  const int r = lane >> 3, u = lane & 7;
+  const float xr = gi_cl[r * 32 + src], yr = gi_cl[np_i + r * 32 + src],
+              zr = gi_cl[2 * np_i + r * 32 + src];
+  const float pxi = __fadd_rn(xr, sx), pyi = __fadd_rn(yr, sy),
+              pzi = __fadd_rn(zr, sz);
   const float *js = gj_f + (size_t)g * GJ;
-  for (int r = 0; r < RI; ++r) {
-    if (!((qmask >> r) & 1)) continue;
-    const float xr = gi_cl[r * 32 + lane], yr = gi_cl[np_i + r * 32 + lane],
-                zr = gi_cl[2 * np_i + r * 32 + lane];
-    const float nxi = __fadd_rn(xr, sx), nyi = __fadd_rn(yr, sy),
-                nzi = __fadd_rn(zr, sz);
-    for (int u = 0; u < GJ; ++u) {
-      const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
-      const float r2 = plain ? pair_r2<BOXKIND, true>(xj, yj, zj, nxi, nyi, nzi, fb)
-                             : pair_r2<BOXKIND, false>(xj, yj, zj, nxi, nyi, nzi, fb);
-      if (r2 < cut) {
-        if (rank == 0)
-          return swapped ? exact_bin<BOXKIND>(xj, yj, zj, xr, yr, zr, fp, hp)
-                         : exact_bin<BOXKIND>(xr, yr, zr, xj, yj, zj, fp, hp);
-        --rank;
-      }
-    }
-  }
-  return -2;  // unreachable: the entry was produced by one of these pairs
+  const float xj = js[u], yj = js[np_j + u], zj = js[2 * np_j + u];
+  const float r2 = plain ? pair_r2<BOXKIND, true>(xj, yj, zj, pxi, pyi, pzi, fb)
+                         : pair_r2<BOXKIND, false>(xj, yj, zj, pxi, pyi, pzi, fb);
+  const unsigned int hm =
+      __ballot_sync(0xffffffffu, ((qmask >> r) & 1) && r2 < cut);
+  if (rank < 0 || rank >= __popc(hm)) return -2;
+  const int owner = (int)__fns(hm, 0, rank + 1);
+  int k = 0;
+  if (lane == owner)
+    k = swapped ? exact_bin<BOXKIND>(xj, yj, zj, xr, yr, zr, fp, hp)
+                : exact_bin<BOXKIND>(xr, yr, zr, xj, yj, zj, fp, hp);
+  return __shfl_sync(0xffffffffu, k, owner);
 }
 
 // R0ZERO: the histogram range starts at 0 (the default, and every BASELINE
@@ -1792,27 +1796,32 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
         }
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(dummy_s), "r"(0u) : "memory");
       }
-      // the rare band failures, after the pipelined loop
-      if (__any_sync(0xffffffffu, failmask != 0ull)) {
-        while (failmask) {
-          const int se = __ffsll((long long)failmask) - 1;
-          failmask &= failmask - 1;
-          const int kk = resolve_entry<BOXKIND>(se, col, mark, glog, nlog, gi_cl,
+      // the rare band failures, after the pipelined loop: lane by lane, entry
+      // by entry, each resolved by the whole warp
+      unsigned int fl = __ballot_sync(0xffffffffu, failmask != 0ull);
+      while (fl) {
+        const int src = __ffs((int)fl) - 1;
+        fl &= fl - 1;
+        unsigned long long fm = __shfl_sync(0xffffffffu, failmask, src);
+        const int scol = __shfl_sync(0xffffffffu, col, src);
+        while (fm) {
+          const int se = __ffsll((long long)fm) - 1;
+          fm &= fm - 1;
+          const int kk = resolve_entry<BOXKIND>(se, scol, mark, glog, nlog, gi_cl,
                                                 np_i, gj_f, np_j, a.swapped, cut,
                                                 fp, &s_hp);
-          ++n_slow;
-          if (kk >= 0) count_bin(kk);
-          // never drop a pair silently (release builds too; rare path):
-          // rdfk_rdf_stats reports it and the engine raises
-          if (kk == -2) {
-            atomicAdd(&a.header->stats[6], 1ull);
-            atomicCAS(&a.header->stats[7], 0ull,
-                      (unsigned long long)CHK_RESOLVE_MISS);
+          if (lane == 0) {
+            ++n_slow;
+            if (kk >= 0) count_bin(kk);
+            // never drop a pair silently (release builds too; rare path):
+            // rdfk_rdf_stats reports it and the engine raises
+            if (kk == -2) {
+              atomicAdd(&a.header->stats[6], 1ull);
+              atomicCAS(&a.header->stats[7], 0ull,
+                        (unsigned long long)CHK_RESOLVE_MISS);
+            }
           }
         }
-        // lanes leave the loop at different times and are not guaranteed to
-        // reconverge by themselves; the log and marks they read are reused
-        // as soon as drain() returns
         __syncwarp();
       }
       qaddr = qbase;
