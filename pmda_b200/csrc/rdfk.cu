@@ -1092,7 +1092,7 @@ constexpr int QS_MAX = 64;    // queue slots per lane (fail mask is 64 bits)
 #define RDFK_GROUP_PARTS 1
 #endif
 #ifndef RDFK_R0FAST_TRI
-#define RDFK_R0FAST_TRI 0
+#define RDFK_R0FAST_TRI 1
 #endif
 #ifndef RDFK_PK_PER_USE
 #define RDFK_PK_PER_USE 1
@@ -1122,7 +1122,10 @@ static_assert(ROT % 2 == 1 && ROT > 0 && ROT < 32, "column step must be odd");
 constexpr int LOGMAX = 32;    // j-groups evaluated between two drains
 constexpr int NSTAGE = 32;    // staged j-groups per warp (one test round)
 constexpr int PAIRS_PER_GROUP = GJ * RI;   // per lane
-constexpr int DW = 16;        // queue entries per lane in flight in the drain
+#ifndef RDFK_DW_ORTHO
+#define RDFK_DW_ORTHO 16
+#endif
+constexpr int DW = RDFK_DW_ORTHO;   // queue entries per lane in flight in the drain
 // (the triclinic instantiation is instruction-cache bound: a narrower loop
 // is 9 % faster there, 16 vs 8 is a wash for the others)
 #ifndef RDFK_DW_TRI
@@ -2548,8 +2551,9 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   const size_t smem =
       (size_t)SM_FIXED + (copies ? (size_t)copies * per_copy + tab_bytes : 0);
   // (debug flag bit 4: the general drain although the range starts at 0)
-  // (the triclinic instantiation is instruction-cache bound: with the fast
-  // drain and its re-scan it ran 1 142 instead of 1 319 frames/s at config 4)
+  // (RDFK_R0FAST_TRI: the triclinic instantiation is instruction-cache bound;
+  // the fast drain pays there only since the fp64 path is warp-cooperative:
+  // 1 358 against 1 334 frames/s at config 4)
   const bool r0zero = copies && hp.r0 == 0.0 && !(debug_flags & 16) &&
                       (BOXKIND != RDFK_BOX_TRI || RDFK_R0FAST_TRI);
   void (*kern)(const PairArgs) = copies ? pair_prune_kernel<BOXKIND, false, false>
