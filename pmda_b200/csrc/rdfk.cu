@@ -1091,6 +1091,9 @@ constexpr int QS_MAX = 64;    // queue slots per lane (fail mask is 64 bits)
 #ifndef RDFK_GROUP_PARTS
 #define RDFK_GROUP_PARTS 1
 #endif
+#ifndef RDFK_DEAD_SLOT_ZERO
+#define RDFK_DEAD_SLOT_ZERO 1
+#endif
 #ifndef RDFK_R0FAST_TRI
 #define RDFK_R0FAST_TRI 1
 #endif
@@ -1691,14 +1694,24 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           float2 t[BW];
 #pragma unroll
           for (int u = 0; u < BW; ++u) v[u] = qcol[(s + u) * 32];
+          const int rem = n - s;   // entries s .. s + rem - 1 are live
 #pragma unroll
           for (int u = 0; u < BW; ++u) {
             kb[u] = __float_as_uint(__fmaf_rd(sqrt_approx(v[u]), inv_dr, MAGIC));
+#if RDFK_DEAD_SLOT_ZERO
+            // dead slots all look at table entry 0 (one broadcast address): the
+            // stale r2 they hold would spread them over the banks (42 % of the
+            // slots of a drained row are dead at config 2, 71 % at config 4:
+            // +1.4 % / +7.9 %; shared memory is 80 % busy in this kernel)
+            uint32_t ta = tab_k + (kb[u] << 3);
+            ta = rem > u ? ta : tab_s32;
+#else
+            const uint32_t ta = tab_k + (kb[u] << 3);
+#endif
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
                          : "=f"(t[u].x), "=f"(t[u].y)
-                         : "r"(tab_k + (kb[u] << 3)));
+                         : "r"(ta));
           }
-          const int rem = n - s;   // entries s .. s + rem - 1 are live
 #pragma unroll
           for (int u = 0; u < BW; ++u) {
             // (one predicate chain and one select: written as `a & b & c ? x
