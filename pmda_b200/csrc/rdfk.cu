@@ -1783,32 +1783,26 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dsum) : "r"(dummy_s) : "memory");
         const int rows = (nmax + BW - 1) / BW * BW;   // slots I walked
         const bool failed = dsum != weight * (unsigned int)(rows - n);
-        if (__any_sync(0xffffffffu, failed)) {
-          // rare: find my failed entries again (same arithmetic, same bits)
-          if (failed) {
-            // (four entries in flight: one at a time, the look-up latencies of
-            // this loop were 8 % of the kernel's stall samples)
-#pragma unroll 1
-            for (int s = 0; s < n; s += 4) {
-              float v[4];
-              bool ok[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u)   // (never past my n entries)
-                v[u] = s + u < n ? qcol[(s + u) * 32] : 0.f;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                uint32_t kb;
-                ok[u] = slot_ok(v[u], true, kb);
-              }
-              unsigned int bad = 0u;
-#pragma unroll
-              for (int u = 0; u < 4; ++u) bad |= ok[u] ? 0u : (1u << u);
-              failmask |= (unsigned long long)bad << s;
-            }
-            // (slots past n were given r2 = 0)
-            failmask &= n >= 64 ? ~0ull : ((1ull << n) - 1ull);
-          }
-          __syncwarp();
+        // rare: find the failed entries again (same arithmetic, same bits).
+        // The whole warp walks the column of one failing lane at a time, lane
+        // t looking at rows t and t + 32 (a lane scanning its own column alone
+        // was 4 - 8 % of the kernel's stall samples).
+        unsigned int fl = __ballot_sync(0xffffffffu, failed);
+        while (fl) {
+          const int src = __ffs((int)fl) - 1;
+          fl &= fl - 1;
+          const int scol = __shfl_sync(0xffffffffu, col, src);
+          const int sn = __shfl_sync(0xffffffffu, n, src);
+          uint32_t kb;
+          const bool bad0 =
+              lane < sn && !slot_ok(q[lane * 32 + scol], true, kb);
+          const bool bad1 =
+              QS > 32 && lane + 32 < sn &&
+              !slot_ok(q[(lane + 32 < QS ? lane + 32 : 0) * 32 + scol], true, kb);
+          const unsigned int m0 = __ballot_sync(0xffffffffu, bad0);
+          const unsigned int m1 = __ballot_sync(0xffffffffu, bad1);
+          if (lane == src) failmask = (unsigned long long)m0 |
+                                      ((unsigned long long)m1 << 32);
         }
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(dummy_s), "r"(0u) : "memory");
       }
