@@ -1717,6 +1717,19 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
             // (one predicate chain and one select: written as `a & b & c ? x
             // : y` the compiler emits three selects)
             uint32_t ha;
+#if RDFK_DEAD_SLOT_ZERO
+            // (a dead slot looked at entry 0, "certainly below r0" = [-inf, 0):
+            // its stale r2 >= 0 is never in there, no liveness test needed)
+            asm("{\n"
+                ".reg .pred p;\n"
+                "setp.ge.f32 p, %1, %2;\n"
+                "setp.lt.and.f32 p, %1, %3, p;\n"
+                "selp.u32 %0, %4, %5, p;\n"
+                "}\n"
+                : "=r"(ha)
+                : "f"(v[u]), "f"(t[u].x), "f"(t[u].y),
+                  "r"(hist_k + (kb[u] << 2)), "r"(dummy_s));
+#else
             asm("{\n"
                 ".reg .pred p;\n"
                 "setp.ge.f32 p, %1, %2;\n"
@@ -1727,6 +1740,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
                 : "=r"(ha)
                 : "f"(v[u]), "f"(t[u].x), "f"(t[u].y), "r"(rem), "r"(u),
                   "r"(hist_k + (kb[u] << 2)), "r"(dummy_s));
+#endif
             asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ha), "r"(weight)
                          : "memory");
           }
@@ -2120,6 +2134,8 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           }
           cp_async_commit_wait_all();
           __syncwarp();
+          // (loading the next group's word while this one is evaluated, by a plain
+          // or a volatile load, was measured twice: no gain)
 #pragma unroll 1
           for (int h = nh - 1; h >= 0; --h) evaluate(h, group_word(h));
         }
