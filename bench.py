@@ -374,7 +374,7 @@ def last_rdf_stats(job):
 
 def committed_ncu():
     """numbers of the committed ncu capture of the pair kernel (profiles/)"""
-    for name in ("r2_traffic.json", "r1h_traffic.json"):
+    for name in ("r2_traffic.json", "r2_before_traffic.json", "r1h_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as fh:
                 d = json.load(fh)
@@ -701,6 +701,9 @@ def run_b200(args):
                            "evaluated pair) / FP32 peak measured live",
         "issue_slot_frac": (ncu or {}).get("issue_slot_frac"),
         "issue_slot_source": (ncu or {}).get("file"),
+        # the resource that is busiest in the committed capture: the kernel
+        # queues, looks up and bins its in-range pairs through shared memory
+        "shared_pipe_frac": (ncu or {}).get("shared_pipe_frac"),
         "traffic": traffic,
         "traffic_source": "%s: dram__bytes_read+write of one ncu --set full "
                           "capture, per frame x frames per launch"

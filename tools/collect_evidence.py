@@ -119,6 +119,12 @@ if os.path.exists(rep):
         "ipc": val("sm__inst_executed.avg.per_cycle_elapsed"),
         "issue_slot_frac":
             val("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+        "shared_pipe_frac": val(
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"
+            ".pct_of_peak_sustained_elapsed") / 100.0,
+        "shared_wavefronts_per_frame":
+            val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") / frames,
+        "warp_instructions_per_frame": val("smsp__inst_executed.sum") / frames,
         "kernel_ms": val("gpu__time_duration.sum") *
             {"ms": 1.0, "us": 1e-3, "s": 1e3, "msecond": 1.0, "usecond": 1e-3,
              "second": 1e3}.get(m["gpu__time_duration.sum"][1], 1.0),
