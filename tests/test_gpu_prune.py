@@ -282,3 +282,37 @@ def test_sliced_tail_work_items_do_not_change_the_counts():
             _gpu(ut, ut.atoms, ut.atoms, 50, (0.0, 11.0), debug=flags | 3), want3)
         np.testing.assert_array_equal(
             _gpu(ut, ut.atoms, ut.atoms, 50, (0.0, 11.0), debug=flags), want3)
+
+
+def _last_stats():
+    import torch
+    from pmda_b200 import engine
+    st = engine._state(torch.device("cuda", torch.cuda.current_device()))
+    ws = st.workspaces[0]
+    ws = ws[(-ws.data_ptr()) % 256:]
+    return _cabi.rdf_stats(ws, st.compute_streams[0].cuda_stream)
+
+
+def test_bins_narrower_than_the_error_bound_take_the_fp64_path():
+    """a frame whose fp32 error bound is not far below the bin width cannot use
+    the drain's candidate bin (it must stay <= nbins): params_kernel sends it
+    through the reference arithmetic, pair by pair"""
+    rng = np.random.default_rng(118)
+    L = 30.0
+    far = np.array([30000.0, -30000.0, 30000.0])
+    pos = (rng.random((2, 500, 3)) * L + far).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    # bound ~ 3e-3 A against dr = 12 / 2000 = 6e-3 A (shared-memory histogram:
+    # the range-from-0 kernel)
+    want, _, _ = oracle_interrdf(u, u.atoms, u.atoms, 2000, (0.0, 12.0), None)
+    for debug in (None, 16):
+        got = _gpu(u, u.atoms, u.atoms, nbins=2000, rng=(0.0, 12.0), debug=debug)
+        np.testing.assert_array_equal(got, want, err_msg="debug flags %r" % debug)
+        assert _last_stats()["all_slow_frames"] == 2
+    # the same atoms near the origin keep the fast path
+    pos = (pos - far.astype(np.float32)).astype(np.float32)
+    u = Universe(pos, [L, L, L, 90, 90, 90])
+    want, _, _ = oracle_interrdf(u, u.atoms, u.atoms, 2000, (0.0, 12.0), None)
+    got = _gpu(u, u.atoms, u.atoms, nbins=2000, rng=(0.0, 12.0))
+    np.testing.assert_array_equal(got, want)
+    assert _last_stats()["all_slow_frames"] == 0
