@@ -57,7 +57,8 @@ const char *rdfk_last_error(void);
  * bit 0: no bounding-box pruning (every group pair is evaluated; hydrogen
  * bonds: no acceptor cell grid), bit 1: no one-shift-per-group arithmetic,
  * bit 2: no Euclidean refinement of the triclinic box test, bit 4: the general
- * drain of the pair kernel's queue although the range starts at 0, bits 8-11: number
+ * drain of the pair kernel's queue although the range starts at 0, bit 5: no
+ * CUDA-graph replay of repeated small calls, bits 8-11: number
  * of slices the last work items of a launch are cut into (0 = the library's
  * own rule).  Results never
  * depend on the flags, throughput does.  An explicit call on purpose -- not an
@@ -279,6 +280,12 @@ int rdfk_zero_async(void *dst, size_t nbytes, void *stream);
  * (all streams, all devices); bench.py reports the difference over its timed
  * region as `gpu_launches`.                                                   */
 unsigned long long rdfk_launch_count(void);
+
+/* number of rdfk_rdf_hist calls answered by replaying a captured CUDA graph
+ * (small calls repeated with identical arguments; see rdfk_set_debug_flags
+ * bit 5).  rdfk_launch_count counts the kernels of a replay like those of a
+ * plain call.                                                                 */
+unsigned long long rdfk_graph_replay_count(void);
 
 /* FP32 roofline denominator: runs a dependent-chain-free FFMA kernel on every
  * SM and returns the achieved TFLOP/s (2 flop per FFMA lane).  Synchronises. */

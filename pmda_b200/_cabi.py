@@ -81,6 +81,8 @@ def _declare(L):
     L.rdfk_zero_async.argtypes = [c_void_p, c_size_t, c_void_p]
     L.rdfk_launch_count.restype = ctypes.c_ulonglong
     L.rdfk_launch_count.argtypes = []
+    L.rdfk_graph_replay_count.restype = ctypes.c_ulonglong
+    L.rdfk_graph_replay_count.argtypes = []
     L.rdfk_measure_fp32_peak.restype = c_int
     L.rdfk_measure_fp32_peak.argtypes = [ctypes.POINTER(c_double), c_void_p]
 
@@ -94,7 +96,8 @@ EXPORTS = ("rdfk_version", "rdfk_last_error", "rdfk_set_debug_flags",
            "rdfk_hbonds_workspace_bytes", "rdfk_hbonds",
            "rdfk_host_hash64_rows", "rdfk_host_gather_rows",
            "rdfk_rdf_stats", "rdfk_rdf_stats_async", "rdfk_zero_async",
-           "rdfk_launch_count", "rdfk_measure_fp32_peak")
+           "rdfk_launch_count", "rdfk_graph_replay_count",
+           "rdfk_measure_fp32_peak")
 
 
 def lib():
@@ -303,6 +306,10 @@ def build_has_checks():
 
 def launch_count():
     return int(lib().rdfk_launch_count())
+
+
+def graph_replay_count():
+    return int(lib().rdfk_graph_replay_count())
 
 
 def measure_fp32_peak(stream=0):

@@ -1004,11 +1004,15 @@ def _run_rdf_part(device, traj, natoms, segs, n_blocks, n_frames, idx1, idx2,
                     tm = _Timer(st)
                     tm.start()
                     stream = st.compute_stream.cuda_stream if cuda else 0
+                    hist_b = hist[b]
                     for kind, lo, hi in _runs(kinds):
-                        be.rdf_hist(xyz[lo:hi], hi - lo, natoms, i1, n1, i2,
-                                    n2, same_group, kind, box_d[lo:hi],
+                        # (only the pointers travel: no upper bounds, and no
+                        # tensor views at all for the usual one-kind batch)
+                        be.rdf_hist(xyz if lo == 0 else xyz[lo:], hi - lo,
+                                    natoms, i1, n1, i2, n2, same_group, kind,
+                                    box_d if lo == 0 else box_d[lo:],
                                     rng[0], rng[1], nbins, edges_d, excl,
-                                    hist[b], ws, stream)
+                                    hist_b, ws, stream)
                     tm.stop()
                     _tp("part: rdfk_rdf_hist (launches)")
                     pipe.mark_compute_done(slot)

@@ -316,3 +316,43 @@ def test_bins_narrower_than_the_error_bound_take_the_fp64_path():
     got = _gpu(u, u.atoms, u.atoms, nbins=2000, rng=(0.0, 12.0))
     np.testing.assert_array_equal(got, want)
     assert _last_stats()["all_slow_frames"] == 0
+
+
+def test_repeated_small_calls_replay_a_graph_with_the_same_integers():
+    """librdfk captures a small call that comes back with identical arguments
+    into a CUDA graph and replays it: same integers, same launch accounting,
+    new coordinates behind the same pointers are seen, debug flag 32 turns it
+    off"""
+    from pmda_b200 import engine
+    from pmda_b200.universe import MemoryTrajectory
+    rng = np.random.default_rng(119)
+    L = 34.0
+    pos = (rng.random((6, 1500, 3)) * L).astype(np.float32)
+    u = Universe(pos.copy(), [L, L, L, 90, 90, 90])
+    want, _, _ = oracle_interrdf(u, u.atoms, u.atoms, 60, (0.0, 11.0), None)
+    engine.clear_cache()
+    replays0 = _cabi.graph_replay_count()
+    per_run = []
+    for rep in range(5):
+        l0 = _cabi.launch_count()
+        got = _gpu(u, u.atoms, u.atoms, nbins=60, rng=(0.0, 11.0))
+        per_run.append(_cabi.launch_count() - l0)
+        np.testing.assert_array_equal(got, want, err_msg="run %d" % rep)
+    assert _cabi.graph_replay_count() - replays0 >= 2, per_run
+    assert len(set(per_run)) == 1, per_run
+    # an in-place edit of the trajectory: the cached block is re-validated by
+    # its hash, re-uploaded, and the replayed graph reads the new frames
+    traj = u.trajectory
+    assert isinstance(traj, MemoryTrajectory)
+    traj.positions[3, 7, :] += np.float32(2.5)
+    want2, _, _ = oracle_interrdf(u, u.atoms, u.atoms, 60, (0.0, 11.0), None)
+    assert (want2 != want).any()
+    for rep in range(3):
+        got = _gpu(u, u.atoms, u.atoms, nbins=60, rng=(0.0, 11.0))
+        np.testing.assert_array_equal(got, want2, err_msg="edited, run %d" % rep)
+    # switched off: no further replays
+    r1 = _cabi.graph_replay_count()
+    for rep in range(3):
+        got = _gpu(u, u.atoms, u.atoms, nbins=60, rng=(0.0, 11.0), debug=32)
+        np.testing.assert_array_equal(got, want2)
+    assert _cabi.graph_replay_count() == r1
