@@ -1172,9 +1172,9 @@ def _finish(hist_np, vol, io, compute, first_launch, blocks, make_result):
     pos = 0
     for b, blk in enumerate(blocks):
         n = len(blk)
-        v = 0.0
-        for x in vol[pos:pos + n]:       # sequential, like `res += r`
-            v = v + float(x)
+        # sequential, like `res += r` frame by frame (np.add.accumulate is a
+        # strict left-to-right scan: the same additions in the same order)
+        v = float(np.add.accumulate(vol[pos:pos + n])[-1]) if n else 0.0
         t_io = io[pos:pos + n].copy()
         t_c = compute[pos:pos + n].copy()
         wait_end = first_launch[b] if np.isfinite(first_launch[b]) \
