@@ -1150,7 +1150,7 @@ constexpr int SM_QB = 2 * 24 * 4;              // my 4 quarter boxes [6][4], x2:
                                                // prune space and Cartesian
 constexpr int SM_CTX = 32 * 4;                 // per-item constants of the box tests
 // Per-instantiation part of the layout.  The triclinic kernel keeps the
-// (negated, shifted) i-atoms of the warp in shared memory instead of
+// (shifted) i-atoms of the warp in shared memory instead of
 // registers: with them in registers ptxas spilled 9 of the 12 coordinates
 // plus loop state to local memory (276 B; ncu r2a: long_scoreboard 1.8
 // cycles per issue on `LDL`s that miss the 23 KB L1 left beside 2 x 109 KB of
@@ -1625,7 +1625,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
 
     // my (shifted) i-atoms
     int cur_code = -1;
-    float nxs[RI], nys[RI], nzs[RI];
+    float pxs[RI], pys[RI], pzs[RI];
     int nlog = 0;
     unsigned int weight = 1u;
     int cls = 0;          // table class of the current pass
@@ -1915,7 +1915,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           if (L::IAT_SMEM) {
             iat[r * 32] = vx; iat[CI + r * 32] = vy; iat[2 * CI + r * 32] = vz;
           } else {
-            nxs[r] = vx; nys[r] = vy; nzs[r] = vz;
+            pxs[r] = vx; pys[r] = vy; pzs[r] = vz;
           }
         }
         cur_code = code;
@@ -1981,22 +1981,22 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           for (int rr = 0; rr < QPP; ++rr) {
             const int r = part * QPP + rr;
             if (!((qm >> r) & 1)) continue;
-            const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
-            const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
-            const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
+            const float pxr = L::IAT_SMEM ? iat[r * 32] : pxs[r];
+            const float pyr = L::IAT_SMEM ? iat[CI + r * 32] : pys[r];
+            const float pzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : pzs[r];
 #pragma unroll
             for (int up = 0; up < GJ / 2; ++up) {
               // (a pack per use: ptxas folds a single-use {a, a} into the
               // FADD2 as a broadcast operand, a shared one costs two moves)
 #if RDFK_PK_PER_USE
-              const uint64_t nx2 = pk2v(nxr, nxr), ny2 = pk2v(nyr, nyr),
-                             nz2 = pk2v(nzr, nzr);
+              const uint64_t px2 = pk2v(pxr, pxr), py2 = pk2v(pyr, pyr),
+                             pz2 = pk2v(pzr, pzr);
 #else
-              const uint64_t nx2 = pk2(nxr, nxr), ny2 = pk2(nyr, nyr),
-                             nz2 = pk2(nzr, nzr);
+              const uint64_t px2 = pk2(pxr, pxr), py2 = pk2(pyr, pyr),
+                             pz2 = pk2(pzr, pzr);
 #endif
-              const uint64_t dx = sub2(xj2[up], nx2), dy = sub2(yj2[up], ny2),
-                             dz = sub2(zj2[up], nz2);
+              const uint64_t dx = sub2(xj2[up], px2), dy = sub2(yj2[up], py2),
+                             dz = sub2(zj2[up], pz2);
               const uint64_t t = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
               float ra, rb;
               unpk2(t, ra, rb);
@@ -2014,9 +2014,9 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           for (int rr = 0; rr < QPP; ++rr) {
             const int r = part * QPP + rr;
             if (!((qm >> r) & 1)) continue;
-            const float nxr = L::IAT_SMEM ? iat[r * 32] : nxs[r];
-            const float nyr = L::IAT_SMEM ? iat[CI + r * 32] : nys[r];
-            const float nzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : nzs[r];
+            const float pxr = L::IAT_SMEM ? iat[r * 32] : pxs[r];
+            const float pyr = L::IAT_SMEM ? iat[CI + r * 32] : pys[r];
+            const float pzr = L::IAT_SMEM ? iat[2 * CI + r * 32] : pzs[r];
 #pragma unroll
             for (int up = 0; up < GJ / 2; ++up) {
               float xa, xb, ya, yb, za, zb;
@@ -2024,9 +2024,9 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
               unpk2(yj2[up], ya, yb);
               unpk2(zj2[up], za, zb);
               q_push(qaddr,
-                     pair_r2<BOXKIND, false>(xa, ya, za, nxr, nyr, nzr, fb), cut);
+                     pair_r2<BOXKIND, false>(xa, ya, za, pxr, pyr, pzr, fb), cut);
               q_push(qaddr,
-                     pair_r2<BOXKIND, false>(xb, yb, zb, nxr, nyr, nzr, fb), cut);
+                     pair_r2<BOXKIND, false>(xb, yb, zb, pxr, pyr, pzr, fb), cut);
             }
           }
         }
