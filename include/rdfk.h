@@ -57,7 +57,8 @@ const char *rdfk_last_error(void);
  * bit 0: no bounding-box pruning (every group pair is evaluated; hydrogen
  * bonds: no acceptor cell grid), bit 1: no one-shift-per-group arithmetic,
  * bit 2: no Euclidean refinement of the triclinic box test, bit 4: the general
- * drain of the pair kernel's queue although the range starts at 0, bit 5: no
+ * candidate-bin arithmetic of the pair kernel's drain although the range
+ * starts at 0, bit 5: no
  * CUDA-graph replay of repeated small calls, bits 8-11: number
  * of slices the last work items of a launch are cut into (0 = the library's
  * own rule).  Results never

@@ -1095,9 +1095,6 @@ constexpr int QS_MAX = 64;    // queue slots per lane (fail mask is 64 bits)
 #ifndef RDFK_DEAD_SLOT_ZERO
 #define RDFK_DEAD_SLOT_ZERO 1
 #endif
-#ifndef RDFK_R0FAST_TRI
-#define RDFK_R0FAST_TRI 1
-#endif
 #ifndef RDFK_PK_PER_USE
 #define RDFK_PK_PER_USE 1
 #endif
@@ -1136,7 +1133,7 @@ constexpr int DW = RDFK_DW_ORTHO;   // queue entries per lane in flight in the d
 #define RDFK_DW_TRI 8
 #endif
 constexpr int DW_TRI = RDFK_DW_TRI;
-// slots per batch of the R0ZERO drain (look-ups in flight per lane)
+// slots per batch of the fast drain (look-ups in flight per lane)
 #ifndef RDFK_DRAIN_BATCH
 #define RDFK_DRAIN_BATCH 8
 #endif
@@ -1343,17 +1340,23 @@ __device__ __noinline__ int resolve_entry(
   return __shfl_sync(0xffffffffu, k, owner);
 }
 
+// GLOBAL_HIST: nbins too large for shared histograms / tables (global atomics,
+// the general drain loop).  Otherwise the fast drain, whose candidate bin of a
+// queue entry is read out of the mantissa of 1.5 * 2^23 + floor(..):
 // R0ZERO: the histogram range starts at 0 (the default, and every BASELINE
-// configuration): the candidate bin of a queue entry is floor(sqrt(r2) / dr),
-// ONE round-down FFMA onto the 1.5 * 2^23 magic number, and it needs no clamp:
-// it cannot be negative, and r2 < r2_cut keeps it <= nbins (params_kernel sends
-// frames whose error bound is not far below the bin width to the fp64 path),
-// for which the tables hold an entry that never decides.
+// configuration): floor(sqrt(r2) / dr) is ONE round-down FFMA onto the magic
+// number and needs no clamp: it cannot be negative, and r2 < r2_cut keeps it
+// <= nbins (params_kernel sends frames whose error bound is not far below the
+// bin width to the fp64 path), for which the tables hold an entry that never
+// decides.  A range that starts above 0 pays two more instructions per slot
+// (the offset cannot ride on the magic number, and everything below r0 - dr is
+// clamped to "bin -1", the tables' "certainly below r0" entry).
 template <int BOXKIND, bool GLOBAL_HIST, bool R0ZERO>
 __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
     const PairArgs a) {
   static_assert(RI == 4 && GJ == 8 && GPC == 16, "written for 4 x 8, 16 groups");
   static_assert(!(GLOBAL_HIST && R0ZERO), "the fast drain reads shared tables");
+  constexpr bool FAST = !GLOBAL_HIST;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ HistParams s_hp;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1406,8 +1409,8 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
   for (int b = tid; b < copies * hstride; b += L::NTHR) hist_s[b] = 0u;
   if (!GLOBAL_HIST)
     for (int b = tid; b < 2 * nbt; b += L::NTHR) tab_s[b] = a.tables[b];
-  if (R0ZERO) {
-    // The fast drain computes a table address from every slot of a drained
+  if (FAST) {
+    // The fast drain computes a candidate bin from every slot of a drained
     // row, dead ones included: they must hold an r2 that was pushed once (or
     // zero), never the garbage shared memory starts with.
     for (int b = lane; b < QS * 32; b += 32) q[b] = 0.f;
@@ -1660,20 +1663,28 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
       const int nmax = __reduce_max_sync(0xffffffffu, n);
       const float inv_dr = fp->inv_dr, koffm = fp->koffm;
       const unsigned int toff = cls ? (unsigned int)nbt + 1u : 1u;
-      // R0ZERO: addresses straight from the bits of kf = 1.5 * 2^23 + k
+      // fast drain: addresses straight from the bits of kf = 1.5 * 2^23 + k
       // (0x4B400000 + k); the constant part wraps modulo 2^32
-      // (opaque to the compiler: it would split the constant off again and
-      // spend a second instruction per slot on adding it back)
       // (a.kbias = 0x4B400000 is a kernel argument so that ptxas cannot split
       // the constant off again and spend a second instruction per slot on
       // adding it back)
       const uint32_t tab_k = tab_s32 + 8u * toff - (a.kbias << 3);
       const uint32_t hist_k = wh_s - (a.kbias << 2);
-      // slot -> live and certainly in its candidate bin (R0ZERO; used by the
-      // drain loop and, bit for bit the same, by the rare re-scan for failed
-      // entries)
+      // the entry that never decides (class 0's last): where dead slots look
+      const uint32_t tab_dead = tab_s32 + 8u * (unsigned int)(nbins + 1);
+      const float koff = __fadd_rn(koffm, 0.5f);   // -r0 / dr
+      // bits of 1.5 * 2^23 + candidate bin (the candidate only has to be right
+      // where the decision band then confirms it)
+      auto cand = [&](float r2) -> uint32_t {
+        const float sq = sqrt_approx(r2);
+        if (R0ZERO) return __float_as_uint(__fmaf_rd(sq, inv_dr, MAGIC));
+        return __float_as_uint(
+            __fadd_rd(fmaxf(__fmaf_rn(sq, inv_dr, koff), -1.f), MAGIC));
+      };
+      // slot -> live and certainly in its candidate bin (used by the rare
+      // re-scan for failed entries, bit for bit what the drain loop does)
       auto slot_ok = [&](float r2, bool live, uint32_t &kb) -> bool {
-        kb = __float_as_uint(__fmaf_rd(sqrt_approx(r2), inv_dr, MAGIC));
+        kb = cand(r2);
         float2 t;
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
                      : "=f"(t.x), "=f"(t.y)
@@ -1681,14 +1692,14 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
         return live & (r2 >= t.x) & (r2 < t.y);
       };
       unsigned long long failmask = 0ull;   // bit s: entry s needs the fp64 path
-      // R0ZERO: batches of BW slots -- all their table look-ups are issued
+      // fast drain: batches of BW slots -- all their table look-ups are issued
       // before the first atomic (the compiler keeps shared loads behind earlier
       // shared atomics: interleaved, every slot waited for its own look-up),
       // and no per-slot bookkeeping: every slot that is not certain (dead ones
       // included) adds `weight` to my dummy word, which is compared with the
       // number of dead slots after the loop
       constexpr int BW = DWL < RDFK_DRAIN_BATCH ? DWL : RDFK_DRAIN_BATCH;
-      if (R0ZERO) {
+      if (FAST) {
         for (int s = 0; s < nmax; s += BW) {
           float v[BW];
           uint32_t kb[BW];
@@ -1698,14 +1709,14 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           const int rem = n - s;   // entries s .. s + rem - 1 are live
 #pragma unroll
           for (int u = 0; u < BW; ++u) {
-            kb[u] = __float_as_uint(__fmaf_rd(sqrt_approx(v[u]), inv_dr, MAGIC));
+            kb[u] = cand(v[u]);
 #if RDFK_DEAD_SLOT_ZERO
-            // dead slots all look at table entry 0 (one broadcast address): the
+            // dead slots all look at ONE table entry (a broadcast address): the
             // stale r2 they hold would spread them over the banks (42 % of the
             // slots of a drained row are dead at config 2, 71 % at config 4:
             // +1.4 % / +7.9 %; shared memory is 80 % busy in this kernel)
             uint32_t ta = tab_k + (kb[u] << 3);
-            ta = rem > u ? ta : tab_s32;
+            ta = rem > u ? ta : tab_dead;
 #else
             const uint32_t ta = tab_k + (kb[u] << 3);
 #endif
@@ -1719,8 +1730,8 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
             // : y` the compiler emits three selects)
             uint32_t ha;
 #if RDFK_DEAD_SLOT_ZERO
-            // (a dead slot looked at entry 0, "certainly below r0" = [-inf, 0):
-            // its stale r2 >= 0 is never in there, no liveness test needed)
+            // (a dead slot looked at the entry that never decides: no
+            // liveness test needed)
             asm("{\n"
                 ".reg .pred p;\n"
                 "setp.ge.f32 p, %1, %2;\n"
@@ -1747,7 +1758,7 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
           }
         }
       }
-      for (int s = 0; !R0ZERO && s < nmax; s += DWL) {
+      for (int s = 0; !FAST && s < nmax; s += DWL) {
         float v[DWL];
 #pragma unroll
         for (int u = 0; u < DWL; ++u) v[u] = qcol[(s + u) * 32];
@@ -1791,9 +1802,9 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
             rem >= DWL ? (unsigned int)((1ull << DWL) - 1ull)
                       : ((1u << (rem > 0 ? rem : 0)) - 1u);
         const unsigned int fail = livemask & ~okmask;
-        if (!R0ZERO) failmask |= (unsigned long long)fail << s;
+        if (!FAST) failmask |= (unsigned long long)fail << s;
       }
-      if (R0ZERO) {
+      if (FAST) {
         unsigned int dsum;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dsum) : "r"(dummy_s) : "memory");
         const int rows = (nmax + BW - 1) / BW * BW;   // slots I walked
@@ -2574,16 +2585,13 @@ static int launch_rdf(const float *xyz, int F, int natoms, const int *idx1,
   a.kbias = 0x4B400000u;
   const size_t smem =
       (size_t)SM_FIXED + (copies ? (size_t)copies * per_copy + tab_bytes : 0);
-  // (debug flag bit 4: the general drain although the range starts at 0)
-  // (RDFK_R0FAST_TRI: the triclinic instantiation is instruction-cache bound;
-  // the fast drain pays there only since the fp64 path is warp-cooperative:
-  // 1 358 against 1 334 frames/s at config 4)
-  const bool r0zero = copies && hp.r0 == 0.0 && !(debug_flags & 16) &&
-                      (BOXKIND != RDFK_BOX_TRI || RDFK_R0FAST_TRI);
-  void (*kern)(const PairArgs) = copies ? pair_prune_kernel<BOXKIND, false, false>
-                                        : pair_prune_kernel<BOXKIND, true, false>;
-  if constexpr (BOXKIND != RDFK_BOX_TRI || RDFK_R0FAST_TRI)
-    if (r0zero) kern = pair_prune_kernel<BOXKIND, false, true>;
+  // (debug flag bit 4: the general candidate-bin arithmetic although the range
+  // starts at 0)
+  const bool r0zero = copies && hp.r0 == 0.0 && !(debug_flags & 16);
+  void (*kern)(const PairArgs) =
+      !copies ? pair_prune_kernel<BOXKIND, true, false>
+              : (r0zero ? pair_prune_kernel<BOXKIND, false, true>
+                        : pair_prune_kernel<BOXKIND, false, false>);
   // the attribute / occupancy queries cost more than a launch: remembered per
   // (device, instantiation, shared-memory size); thread_local, no locking
   struct OccCache { int dev; void *fn; size_t smem; int occ; };

@@ -2,7 +2,8 @@
 the box tests and the one-shift-per-group fast path could get wrong must still
 give the oracle's integers.  rdfk_set_debug_flags (bit 0: no pruning, bit 1: no shifted
 variant, bit 2: no Euclidean refinement of the triclinic box test, bit 4: the
-general drain although the range starts at 0) is read by librdfk on every call;
+general candidate-bin arithmetic although the range starts at 0) is read by
+librdfk on every call;
 results must not depend on it."""
 import os
 
