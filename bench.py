@@ -386,13 +386,18 @@ def committed_ncu():
 
 
 # -- the other BASELINE configurations ---------------------------------------
-CONFIG_FRAMES = {1: ("total", 100), 3: ("per_gpu", 400), 4: ("per_gpu", 32),
-                 5: ("per_gpu", 24)}
+# (configs[2] at the trajectory length BASELINE.json names: with 400 frames the
+# fixed cost of a run() hid a third of the throughput, 72 000 against 112 000
+# frames/s end to end)
+# configs[3] / [4]: 384 MB / 768 MB of frames per GPU, enough for the first
+# upload (the only one no kernel hides) not to dominate a run
+CONFIG_FRAMES = {1: ("total", 100), 3: ("per_gpu", 2000), 4: ("per_gpu", 128),
+                 5: ("per_gpu", 64)}
 CONFIG_NAMES = {
     1: "BASELINE configs[0]: InterRDF O-O, 3,000-water box, 100 frames, "
        "nbins=75, range 0-15 A, orthorhombic",
     3: "BASELINE configs[2]: InterRDF_s, 64 ion-water site pairs (1 x 256), "
-       "50k-atom box, nbins=75",
+       "50k-atom box, 2000 frames, nbins=75",
     4: "BASELINE configs[3]: InterRDF, 250k-atom triclinic box "
        "(152.3 A, 60/60/90), nbins=75, frame-sharded",
     5: "BASELINE configs[4]: InterRDF 1k x 1M membrane-like box, nbins=75, "
