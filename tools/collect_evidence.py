@@ -12,6 +12,7 @@ tracked files under profiles/:
   profiles/r2_traffic.json           DRAM bytes per frame + issue-slot use of
                                      the ortho capture (bench.py reads it)
   profiles/r2_launches_bench_small.csv
+  profiles/r2_full_length.json       tools/bench_full_length.py, one line per config
 """
 import csv
 import json
@@ -131,6 +132,10 @@ if os.path.exists(rep):
     }
     with open(os.path.join(PROF, "r2_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1)
+src = os.path.join(OUT, tag + "_full_length.txt")
+if os.path.exists(src):
+    with open(src) as a, open(os.path.join(PROF, "r2_full_length.json"), "w") as b:
+        b.write(a.read())
 src = os.path.join(OUT, tag + "_launches_bench_small.csv")
 if os.path.exists(src):
     with open(src) as a, open(os.path.join(PROF, "r2_launches_bench_small.csv"), "w") as b:

@@ -11,6 +11,7 @@ python tools/cpu_configs.py > $o/${tag}_cpu_configs.txt 2>&1
 python tools/bench_contacts.py > $o/${tag}_contacts.txt 2>&1
 python tools/bench_hbonds.py > $o/${tag}_hbonds.txt 2>&1
 python tools/probe_host_time.py 1 3 > $o/${tag}_host_time.txt 2>&1
+python tools/bench_full_length.py 2 3 4 5 > $o/${tag}_full_length.txt 2>&1
 # ncu: each only after the same command exited 0 without it
 python tools/bench_kernel.py 4 > $o/${tag}_plain4.txt 2>&1 && ncu --set full --clock-control none --import-source on -k regex:pair_prune -s 4 -c 1 -f -o $o/${tag}_tri python tools/bench_kernel.py 4 > $o/${tag}_ncu_tri.log 2>&1
 python tools/bench_kernel.py 2 > $o/${tag}_plain2.txt 2>&1 && ncu --set full --clock-control none --import-source on -k regex:pair_prune -s 4 -c 1 -f -o $o/${tag}_ortho python tools/bench_kernel.py 2 > $o/${tag}_ncu_ortho.log 2>&1
