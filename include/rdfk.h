@@ -263,7 +263,8 @@ int rdfk_host_sites_finish(const unsigned int *count_host, int n_blocks,
  * part of the arithmetic restated without a pinned reference: see DESIGN.md),
  * [5] frames that held such atoms, [6] internal consistency violations (a
  * queue entry whose pair could not be found again -- always counted -- and,
- * in RDFK_CHECK builds, queue / log bound violations; must be 0), [7] code of
+ * in RDFK_CHECK builds, queue / log / staging / table-index bound violations;
+ * must be 0), [7] code of
  * the first violation.  Synchronises `stream`.                               */
 int rdfk_rdf_stats(const void *workspace, unsigned long long *out_host,
                    void *stream);

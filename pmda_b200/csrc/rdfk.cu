@@ -173,6 +173,8 @@ enum {
   CHK_RESOLVE_MISS = 3,     // resolve_entry() did not find the entry's pair
                             // (counted in release builds too)
   CHK_STAGE_SLOT = 5,       // staged group slot / index out of range
+  CHK_TABLE_INDEX = 6,      // candidate bin of a live queue entry outside
+                            // [-1, nbins]
 };
 
 struct WsLayout {
@@ -1716,6 +1718,11 @@ __global__ __launch_bounds__(Lay<BOXKIND>::NTHR, 2) void pair_prune_kernel(
 #pragma unroll
           for (int u = 0; u < BW; ++u) {
             kb[u] = cand(v[u]);
+            // (-1 <= candidate bin <= nbins: the look-up stays inside the table)
+            RDFK_CHECK_THAT(a.header,
+                            !(rem > u) || kb[u] - a.kbias + 1u <=
+                                              (unsigned int)(nbins + 1),
+                            CHK_TABLE_INDEX);
 #if RDFK_DEAD_SLOT_ZERO
             // dead slots all look at ONE table entry (a broadcast address): the
             // stale r2 they hold would spread them over the banks (42 % of the

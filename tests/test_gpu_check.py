@@ -40,7 +40,7 @@ def stats():
 
 def run(u, g1, g2, nbins, rng, excl=None, oracle=True):
     want = None
-    for flags in (0, 1, 2, 3, 4):
+    for flags in (0, 1, 2, 3, 4, 16):
         old = _cabi.set_debug_flags(flags)
         try:
             r = InterRDF(g1, g2, nbins=nbins, range=rng,
@@ -62,6 +62,12 @@ pos = (rng.random((3, 2500, 3)) * L).astype(np.float32)
 u = Universe(pos, [L, L, L, 90, 90, 90])
 run(u, u.atoms, u.atoms, 75, (0.0, 12.0))
 run(u, u.atoms[:700], u.atoms[700:], 200, (1.0, 9.0), excl=None)
+# many narrow bins far from the origin: candidate bins near the table's end,
+# wide decision bands, many fp64 re-checks
+far = (pos[:2, :1200] + np.float32(700.0)).astype(np.float32)
+uf = Universe(far, [L, L, L, 90, 90, 90])
+run(uf, uf.atoms, uf.atoms, 3000, (0.0, 12.0))
+run(uf, uf.atoms, uf.atoms, 3000, (2.0, 12.0))
 # everything in range of everything (cut-off > L/2): queues saturate
 run(u, u.atoms[:1500], u.atoms[:1500], 40, (0.0, 14.9))
 # points piled on a few sites: every pair of a group is a hit
