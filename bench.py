@@ -709,6 +709,9 @@ def run_b200(args):
         # the resource that is busiest in the committed capture: the kernel
         # queues, looks up and bins its in-range pairs through shared memory
         "shared_pipe_frac": (ncu or {}).get("shared_pipe_frac"),
+        "binding_resource": "shared-memory pipe (shared_pipe_frac) and issue "
+                            "slots (issue_slot_frac): neither HBM nor the FMA "
+                            "pipe bounds this kernel (DESIGN.md section 4)",
         "traffic": traffic,
         "traffic_source": "%s: dram__bytes_read+write of one ncu --set full "
                           "capture, per frame x frames per launch"
