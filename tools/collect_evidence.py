@@ -132,6 +132,15 @@ if os.path.exists(rep):
     }
     with open(os.path.join(PROF, "r2_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1)
+for name, dest in ((tag + "_bench_reference.json", "r2_bench_reference_n1.json"),
+                   (tag + "_bench_reference_n8.json", "r2_bench_reference_n8.json")):
+    p = os.path.join(OUT, name)
+    if os.path.exists(p):
+        try:
+            with open(os.path.join(PROF, dest), "w") as fh:
+                json.dump(last_json(p), fh, indent=1)
+        except Exception:
+            pass
 src = os.path.join(OUT, tag + "_full_length.txt")
 if os.path.exists(src):
     with open(src) as a, open(os.path.join(PROF, "r2_full_length.json"), "w") as b:
