@@ -562,8 +562,12 @@ def _box_rows_uncached(dims, n):
 def _runs(kinds):
     """consecutive runs of equal box kind -> [(kind, lo, hi)]"""
     kinds = np.asarray(kinds)
-    if len(kinds) == 0:
+    n = len(kinds)
+    if n == 0:
         return []
+    k0 = kinds[0]
+    if k0 == kinds[n - 1] and (kinds == k0).all():   # the usual case: one run
+        return [(int(k0), 0, n)]
     cuts = np.flatnonzero(kinds[1:] != kinds[:-1]) + 1
     lo = np.concatenate(([0], cuts))
     hi = np.concatenate((cuts, [len(kinds)]))
