@@ -2774,10 +2774,17 @@ extern "C" int rdfk_rdf_hist(const float *xyz, int F, int natoms,
   }
   slot->stamp = ++stamp;
   if (slot->exec) {
-    CUDA_TRY(cudaGraphLaunch(slot->exec, st));
-    COUNT_LAUNCH(slot->launches);
-    __atomic_fetch_add(&g_graph_replays, 1ull, __ATOMIC_RELAXED);
-    return RDFK_OK;
+    if (cudaGraphLaunch(slot->exec, st) == cudaSuccess) {
+      COUNT_LAUNCH(slot->launches);
+      __atomic_fetch_add(&g_graph_replays, 1ull, __ATOMIC_RELAXED);
+      return RDFK_OK;
+    }
+    // a replay that cannot be launched: drop the graph, launch as usual
+    (void)cudaGetLastError();
+    cudaGraphExecDestroy(slot->exec);
+    slot->exec = nullptr;
+    slot->bad = 1;
+    return launch();
   }
   if (++slot->seen < 2 || slot->bad) return launch();
   // second call with this key: capture, instantiate, replay
@@ -2792,9 +2799,12 @@ extern "C" int rdfk_rdf_hist(const float *xyz, int F, int natoms,
         cudaGraphInstantiate(&slot->exec, graph, 0) == cudaSuccess) {
       cudaGraphDestroy(graph);
       slot->launches = counted;
-      CUDA_TRY(cudaGraphLaunch(slot->exec, st));
-      __atomic_fetch_add(&g_graph_replays, 1ull, __ATOMIC_RELAXED);
-      return RDFK_OK;
+      if (cudaGraphLaunch(slot->exec, st) == cudaSuccess) {
+        __atomic_fetch_add(&g_graph_replays, 1ull, __ATOMIC_RELAXED);
+        return RDFK_OK;
+      }
+      cudaGraphExecDestroy(slot->exec);
+      graph = nullptr;
     }
     // nothing ran during the capture: forget the graph, launch as usual
     if (graph) cudaGraphDestroy(graph);
